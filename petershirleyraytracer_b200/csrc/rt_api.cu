@@ -1,0 +1,552 @@
+// rt_api.cu -- the C ABI of include/rt.h over the sm_100a kernels in rt_kernels.cuh.
+// Host side only flattens, uploads, launches and copies; there is no CPU implementation of the path.
+#include "../../include/rt.h"
+#include "rt_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define RT_CUDA(expr)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t e__ = (expr);                                                                           \
+        if (e__ != cudaSuccess)                                                                             \
+            return fail(RT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                  \
+    } while (0)
+
+struct DeviceGuard {  // the caller (e.g. torch) keeps its own current device
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+struct DevBuf {  // scoped device allocation
+    T* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, (n ? n : 1) * sizeof(T)); }
+};
+
+}  // namespace
+
+struct rt_scene {
+    int device = 0;
+    int n = 0, npad = 0;
+    int sm_count = 0;
+    float4* d_filt = nullptr;
+    double4* d_exact = nullptr;
+    unsigned int* d_tile_counter = nullptr;   // work-queue head of the persistent warps
+    unsigned long long* d_stats = nullptr;
+    void* d_accum = nullptr; size_t accum_cap = 0;   // fixed-point radiance per tile pixel (+ chunk counters behind it)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // scratch for the host-buffer entry points (grow only)
+    void* d_frame = nullptr; size_t frame_cap = 0;
+    void* d_sum = nullptr;   size_t sum_cap = 0;
+    // last asynchronous render
+    bool pending = false;
+    cudaStream_t last_stream = nullptr;
+    int last_mode = 0;
+    uint64_t last_launches = 0;
+};
+
+namespace {
+
+float round_down_f32(double v) {
+    float f = (float)v;
+    if ((double)f > v) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+
+int check_params(const rt_params* p) {
+    if (!p) return fail(RT_ERR_INVALID, "params is NULL");
+    if (p->width < 2 || p->height < 2) return fail(RT_ERR_INVALID, "width and height must be >= 2 (u,v divide by W-1, H-1)");
+    if ((int64_t)p->width * p->height > (int64_t)1 << 30) return fail(RT_ERR_INVALID, "frame too large");
+    if (p->spp < 1 || p->spp > (1 << 24)) return fail(RT_ERR_INVALID, "spp must be in [1, 2^24]");
+    if (p->max_depth > 1000) return fail(RT_ERR_INVALID, "max_depth must be <= 1000");
+    if (p->shard_count < 1 || p->shard_rank < 0 || p->shard_rank >= p->shard_count)
+        return fail(RT_ERR_INVALID, "bad shard_rank / shard_count");
+    if (p->scan_mode < 0 || p->scan_mode > RT_SCAN_AUTO) return fail(RT_ERR_INVALID, "bad scan_mode");
+    return RT_OK;
+}
+
+void tile_layout(const rt_params* p, rt_tile_layout* L) {
+    L->tile_w = rt::kTileW; L->tile_h = rt::kTileH;
+    L->tiles_x = (p->width + rt::kTileW - 1) / rt::kTileW;
+    L->tiles_y = (p->height + rt::kTileH - 1) / rt::kTileH;
+    L->tiles_total = L->tiles_x * L->tiles_y;
+    L->tiles_per_shard = (L->tiles_total + p->shard_count - 1) / p->shard_count;
+    L->shard_bytes = (int64_t)L->tiles_per_shard * rt::kTilePix * 4;
+}
+
+// AUTO -> FILTERED while the cull array fits in shared memory (the BVH path takes over above that).
+int resolve_scan_mode(const rt_scene* sc, int mode, int* out) {
+    if (mode == RT_SCAN_AUTO) mode = RT_SCAN_FILTERED;
+    if (mode == RT_SCAN_BVH) return fail(RT_ERR_UNSUPPORTED, "BVH traversal is not built yet");
+    if (mode == RT_SCAN_FILTERED && sc->npad > rt::kMaxLinear)
+        return fail(RT_ERR_UNSUPPORTED, "linear cull scan holds at most 4096 spheres in shared memory; use RT_SCAN_EXACT or the BVH");
+    *out = mode;
+    return RT_OK;
+}
+
+rt::SceneDev scene_dev(const rt_scene* sc, int mode) {
+    rt::SceneDev d;
+    d.filt = sc->d_filt; d.exact = sc->d_exact; d.n = sc->n;
+    d.npad = (mode == RT_SCAN_FILTERED) ? sc->npad : 0;  // EXACT stages nothing
+    return d;
+}
+
+int grow(void** p, size_t* cap, size_t need) {
+    if (*cap >= need) return RT_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    RT_CUDA(cudaMalloc(p, need));
+    *cap = need;
+    return RT_OK;
+}
+
+int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* d_rgba, void* d_sum,
+                  cudaStream_t stream) {
+    int mode = 0;
+    int rc = resolve_scan_mode(sc, p->scan_mode, &mode);
+    if (rc) return rc;
+    rt_tile_layout L;
+    tile_layout(p, &L);
+    rt::RenderArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.sc = scene_dev(sc, mode);
+    for (int c = 0; c < 3; ++c) {
+        a.cam_org[c] = cam->origin[c]; a.cam_llc[c] = cam->lower_left_corner[c];
+        a.cam_hor[c] = cam->horizontal[c]; a.cam_ver[c] = cam->vertical[c];
+    }
+    a.tmin = p->tmin;
+    a.W = p->width; a.H = p->height; a.spp = p->spp; a.max_depth = p->max_depth;
+    a.key0 = (uint32_t)p->seed; a.key1 = (uint32_t)(p->seed >> 32);
+    a.jitter = p->jitter; a.scan_mode = mode;
+    a.early_out = (p->early_out && p->tmin == 0.0) ? 1 : 0;  // the cut is only exact for tmin == 0
+    a.tiles_x = L.tiles_x; a.tiles_total = L.tiles_total;
+    a.shard_rank = p->shard_rank; a.shard_count = p->shard_count;
+    a.tiles_local = (L.tiles_total - p->shard_rank + p->shard_count - 1) / p->shard_count;
+    a.compact_out = p->shard_count > 1;
+    a.out = (uchar4*)d_rgba; a.sum_out = (double*)d_sum;
+    a.unit_counter = sc->d_tile_counter; a.stats = sc->d_stats;
+
+    int R = p->reserved[0];
+    if (R == 0) R = 2;
+    if (R != 1 && R != 2) return fail(RT_ERR_INVALID, "reserved[0] (paths per lane) must be 0, 1 or 2");
+    const rt::SmemLayout S = rt::smem_layout(a.sc.npad, R);
+    auto kern = (R == 1) ? rt::render_kernel<1> : rt::render_kernel<2>;
+    RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
+    int per_sm = 0;
+    RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, rt::kThreads, S.total));
+    if (per_sm < 1) return fail(RT_ERR_CUDA, "render kernel does not fit on an SM");
+    const int full_grid = sc->sm_count * per_sm;  // persistent: every resident warp pulls work units
+
+    // Work units = (tile, sample chunk).  Enough chunks that every resident warp sees ~64 units (the queue
+    // then balances to ~1%), but at least 8 samples per pixel and chunk; reserved[1] overrides (tests).
+    const int warps = full_grid * rt::kWarps;
+    int chunks = (64 * warps + a.tiles_local - 1) / (a.tiles_local > 0 ? a.tiles_local : 1);
+    const int max_chunks = (p->spp + 7) / 8;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (p->reserved[1] > 0) chunks = p->reserved[1] < p->spp ? p->reserved[1] : p->spp;
+    if (chunks < 1) chunks = 1;
+    a.chunk_spp = (p->spp + chunks - 1) / chunks;
+    a.chunks = (p->spp + a.chunk_spp - 1) / a.chunk_spp;  // no empty chunk
+    a.units_local = a.tiles_local * a.chunks;
+    int grid = full_grid;
+    const int need = (a.units_local + rt::kWarps - 1) / rt::kWarps;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+
+    if (a.chunks > 1) {
+        const size_t acc_bytes = (size_t)a.tiles_local * rt::kTilePix * 3 * sizeof(unsigned long long);
+        const size_t done_bytes = (size_t)a.tiles_local * sizeof(unsigned int);
+        int rc2 = grow(&sc->d_accum, &sc->accum_cap, acc_bytes + done_bytes);
+        if (rc2) return rc2;
+        a.accum = (unsigned long long*)sc->d_accum;
+        a.tile_done = (unsigned int*)((char*)sc->d_accum + acc_bytes);
+        RT_CUDA(cudaMemsetAsync(sc->d_accum, 0, acc_bytes + done_bytes, stream));
+    }
+    RT_CUDA(cudaMemsetAsync(sc->d_tile_counter, 0, sizeof(unsigned int), stream));
+    RT_CUDA(cudaMemsetAsync(sc->d_stats, 0, rt::kNumStats * sizeof(unsigned long long), stream));
+    if (a.compact_out) RT_CUDA(cudaMemsetAsync(d_rgba, 0, (size_t)L.shard_bytes, stream));
+    RT_CUDA(cudaEventRecord(sc->ev0, stream));
+    kern<<<grid, rt::kThreads, S.total, stream>>>(a);
+    RT_CUDA(cudaGetLastError());
+    RT_CUDA(cudaEventRecord(sc->ev1, stream));
+    sc->pending = true; sc->last_stream = stream; sc->last_mode = mode; sc->last_launches = 1;
+    return RT_OK;
+}
+
+int finish_render(rt_scene* sc, rt_stats* st) {
+    if (!sc->pending) return fail(RT_ERR_INVALID, "no render in flight on this scene");
+    RT_CUDA(cudaEventSynchronize(sc->ev1));
+    sc->pending = false;
+    if (!st) return RT_OK;
+    unsigned long long h[rt::kNumStats];
+    RT_CUDA(cudaMemcpy(h, sc->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+    float ms = 0.f;
+    RT_CUDA(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1));
+    std::memset(st, 0, sizeof *st);
+    st->kernel_ms = ms;
+    st->samples = h[rt::ST_SAMPLES]; st->casts = h[rt::ST_CASTS];
+    st->sphere_tests = (sc->last_mode == RT_SCAN_FILTERED) ? h[rt::ST_CASTS] * (uint64_t)sc->n : 0;
+    st->node_tests = h[rt::ST_NODE_TESTS]; st->exact_tests = h[rt::ST_EXACT_TESTS];
+    st->black = h[rt::ST_BLACK]; st->early_outs = h[rt::ST_EARLY_OUTS];
+    st->primary_hits = h[rt::ST_PRIMARY_HITS]; st->overflows = h[rt::ST_OVERFLOWS];
+    st->launches = sc->last_launches;
+    return RT_OK;
+}
+
+int batch_grid(const rt_scene* sc, int nrays) {
+    int g = (nrays + rt::kThreads - 1) / rt::kThreads;
+    const int cap = sc->sm_count * 4;
+    return g < 1 ? 1 : (g > cap ? cap : g);
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_abi_version(void) { return RT_ABI_VERSION; }
+const char* rt_last_error(void) { return g_err.c_str(); }
+
+int rt_device_info(int32_t device, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, char* name, int32_t name_cap) {
+    cudaDeviceProp prop;
+    RT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (name && name_cap > 0) { std::strncpy(name, prop.name, (size_t)name_cap - 1); name[name_cap - 1] = 0; }
+    return RT_OK;
+}
+
+int rt_upload_scene(const double* centres_xyz, const double* radii, int32_t n, int32_t device, rt_scene** out) {
+    if (!out) return fail(RT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n < 0 || (n > 0 && (!centres_xyz || !radii))) return fail(RT_ERR_INVALID, "bad sphere arrays");
+    if (n > 65535) return fail(RT_ERR_UNSUPPORTED, "more than 65535 spheres needs the BVH path (not built yet)");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed (no CUDA device?)");
+    rt_scene* sc = new (std::nothrow) rt_scene();
+    if (!sc) return fail(RT_ERR_NOMEM, "host allocation failed");
+    sc->device = device; sc->n = n;
+    sc->npad = (n + rt::kScanUnroll - 1) / rt::kScanUnroll * rt::kScanUnroll;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete sc; return fail(RT_ERR_CUDA, "cudaGetDeviceProperties failed"); }
+    sc->sm_count = prop.multiProcessorCount;
+
+    // FP32 cull entries {c, |c|^2 - r^2 - E_k}: computed in FP64, constant term rounded DOWN.
+    std::vector<float4> filt((size_t)sc->npad > 0 ? sc->npad : 1);
+    std::vector<double4> exact((size_t)n > 0 ? n : 1);
+    for (int k = 0; k < sc->npad; ++k) {
+        float4 f;
+        if (k < n) {
+            const double cx = centres_xyz[3 * k], cy = centres_xyz[3 * k + 1], cz = centres_xyz[3 * k + 2], r = radii[k];
+            const double a2 = cx * cx + cy * cy + cz * cz, r2 = r * r;
+            const double Ek = rt::kCullEps * (rt::kCullKc * a2 + rt::kCullKr * r2);
+            f.x = (float)cx; f.y = (float)cy; f.z = (float)cz;
+            f.w = round_down_f32(a2 - r2 - Ek);
+            exact[k] = make_double4(cx, cy, cz, r);
+        } else {
+            f.x = f.y = f.z = 0.f;
+            f.w = INFINITY;  // q = +inf -> D = -inf: never passes
+        }
+        filt[k] = f;
+    }
+    int rc = RT_OK;
+    do {
+        if (cudaMalloc(&sc->d_filt, filt.size() * sizeof(float4)) != cudaSuccess ||
+            cudaMalloc(&sc->d_exact, exact.size() * sizeof(double4)) != cudaSuccess ||
+            cudaMalloc(&sc->d_tile_counter, sizeof(unsigned int)) != cudaSuccess ||
+            cudaMalloc(&sc->d_stats, rt::kNumStats * sizeof(unsigned long long)) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
+        if (cudaMemcpy(sc->d_filt, filt.data(), filt.size() * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(sc->d_exact, exact.data(), exact.size() * sizeof(double4), cudaMemcpyHostToDevice) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
+        if (cudaEventCreate(&sc->ev0) != cudaSuccess || cudaEventCreate(&sc->ev1) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
+    } while (0);
+    if (rc != RT_OK) {
+        const std::string msg = std::string("scene upload: ") + cudaGetErrorString(cudaGetLastError());
+        rt_free_scene(sc);
+        return fail(rc, msg);
+    }
+    *out = sc;
+    return RT_OK;
+}
+
+void rt_free_scene(rt_scene* sc) {
+    if (!sc) return;
+    DeviceGuard guard(sc->device);
+    if (sc->pending) cudaEventSynchronize(sc->ev1);
+    cudaFree(sc->d_filt); cudaFree(sc->d_exact); cudaFree(sc->d_tile_counter); cudaFree(sc->d_stats);
+    cudaFree(sc->d_frame); cudaFree(sc->d_sum); cudaFree(sc->d_accum);
+    if (sc->ev0) cudaEventDestroy(sc->ev0);
+    if (sc->ev1) cudaEventDestroy(sc->ev1);
+    delete sc;
+}
+
+int rt_scene_size(const rt_scene* sc) { return sc ? sc->n : RT_ERR_INVALID; }
+
+int rt_get_tile_layout(const rt_params* p, rt_tile_layout* out) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (!out) return fail(RT_ERR_INVALID, "out is NULL");
+    tile_layout(p, out);
+    return RT_OK;
+}
+
+int rt_render_device(const rt_scene* scene, const rt_camera* cam, const rt_params* p, void* d_rgba, void* d_sum,
+                     void* stream) {
+    if (!scene || !cam || !d_rgba) return fail(RT_ERR_INVALID, "NULL argument");
+    int rc = check_params(p);
+    if (rc) return rc;
+    rt_scene* sc = const_cast<rt_scene*>(scene);
+    DeviceGuard guard(sc->device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->ev1));
+    if (d_sum && p->shard_count > 1) return fail(RT_ERR_INVALID, "radiance sums are only available for shard_count == 1");
+    return launch_render(sc, cam, p, d_rgba, d_sum, (cudaStream_t)stream);
+}
+
+int rt_render_finish(const rt_scene* scene, rt_stats* st) {
+    if (!scene) return fail(RT_ERR_INVALID, "NULL scene");
+    rt_scene* sc = const_cast<rt_scene*>(scene);
+    DeviceGuard guard(sc->device);
+    return finish_render(sc, st);
+}
+
+int rt_render(const rt_scene* scene, const rt_camera* cam, const rt_params* p, uint8_t* rgba_out, double* sum_out,
+              rt_stats* st) {
+    if (!scene || !cam || !rgba_out) return fail(RT_ERR_INVALID, "NULL argument");
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (p->shard_count != 1) return fail(RT_ERR_INVALID, "rt_render renders whole frames; use rt_render_device for shards");
+    rt_scene* sc = const_cast<rt_scene*>(scene);
+    DeviceGuard guard(sc->device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    const size_t npix = (size_t)p->width * p->height;
+    rc = grow(&sc->d_frame, &sc->frame_cap, npix * 4);
+    if (rc) return rc;
+    if (sum_out) { rc = grow(&sc->d_sum, &sc->sum_cap, npix * 3 * sizeof(double)); if (rc) return rc; }
+    if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->ev1));
+    rc = launch_render(sc, cam, p, sc->d_frame, sum_out ? sc->d_sum : nullptr, nullptr);
+    if (rc) return rc;
+    rc = finish_render(sc, st);
+    if (rc) return rc;
+    RT_CUDA(cudaMemcpy(rgba_out, sc->d_frame, npix * 4, cudaMemcpyDeviceToHost));
+    if (sum_out) RT_CUDA(cudaMemcpy(sum_out, sc->d_sum, npix * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_deinterleave(const rt_params* p, const void* d_gathered, void* d_rgba, int32_t device, void* stream) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (!d_gathered || !d_rgba) return fail(RT_ERR_INVALID, "NULL buffer");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    rt_tile_layout L;
+    tile_layout(p, &L);
+    const size_t npix = (size_t)p->width * p->height;
+    int grid = (int)((npix + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    rt::deinterleave_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uchar4*)d_gathered, (uchar4*)d_rgba, p->width,
+                                                                    p->height, L.tiles_x, L.tiles_total, p->shard_count,
+                                                                    L.tiles_per_shard);
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
+static int run_hit_kernel(rt_scene* sc, int mode_kernel, rt::RayBatchArgs& a, int nrays) {
+    const rt::SmemLayout S = rt::smem_layout(a.sc.npad, 1);
+    auto kern = mode_kernel == 0 ? rt::hit_kernel<0> : rt::hit_kernel<1>;
+    RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
+    kern<<<batch_grid(sc, nrays), rt::kThreads, S.total>>>(a);
+    RT_CUDA(cudaGetLastError());
+    RT_CUDA(cudaDeviceSynchronize());
+    return RT_OK;
+}
+
+int rt_primary_hits(const rt_scene* scene, const rt_camera* cam, const rt_params* p, int32_t* idx_out, double* t_out) {
+    if (!scene || !cam || !idx_out || !t_out) return fail(RT_ERR_INVALID, "NULL argument");
+    int rc = check_params(p);
+    if (rc) return rc;
+    rt_scene* sc = const_cast<rt_scene*>(scene);
+    DeviceGuard guard(sc->device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    int mode = 0;
+    rc = resolve_scan_mode(sc, p->scan_mode, &mode);
+    if (rc) return rc;
+    const int npix = p->width * p->height;
+    DevBuf<int32_t> d_idx; DevBuf<double> d_t;
+    RT_CUDA(d_idx.alloc(npix)); RT_CUDA(d_t.alloc(npix));
+    rt::RayBatchArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.sc = scene_dev(sc, mode); a.nrays = npix; a.tmin = p->tmin; a.tmax = INFINITY; a.scan_mode = mode;
+    for (int c = 0; c < 3; ++c) {
+        a.cam_org[c] = cam->origin[c]; a.cam_llc[c] = cam->lower_left_corner[c];
+        a.cam_hor[c] = cam->horizontal[c]; a.cam_ver[c] = cam->vertical[c];
+    }
+    a.W = p->width; a.H = p->height; a.idx_out = d_idx.p; a.t_out = d_t.p;
+    rc = run_hit_kernel(sc, 1, a, npix);
+    if (rc) return rc;
+    RT_CUDA(cudaMemcpy(idx_out, d_idx.p, (size_t)npix * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    RT_CUDA(cudaMemcpy(t_out, d_t.p, (size_t)npix * sizeof(double), cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_hit(const rt_scene* scene, const double* org, const double* dir, int32_t nrays, double tmin, double tmax,
+           int32_t scan_mode, int32_t* idx_out, double* rec_out) {
+    if (!scene || !org || !dir || !idx_out || !rec_out || nrays < 0) return fail(RT_ERR_INVALID, "bad argument");
+    if (nrays == 0) return RT_OK;
+    rt_scene* sc = const_cast<rt_scene*>(scene);
+    DeviceGuard guard(sc->device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    int mode = 0;
+    int rc = resolve_scan_mode(sc, scan_mode, &mode);
+    if (rc) return rc;
+    DevBuf<double> d_org, d_dir, d_rec; DevBuf<int32_t> d_idx;
+    RT_CUDA(d_org.alloc(3 * (size_t)nrays)); RT_CUDA(d_dir.alloc(3 * (size_t)nrays));
+    RT_CUDA(d_rec.alloc(8 * (size_t)nrays)); RT_CUDA(d_idx.alloc(nrays));
+    RT_CUDA(cudaMemcpy(d_org.p, org, 3 * (size_t)nrays * sizeof(double), cudaMemcpyHostToDevice));
+    RT_CUDA(cudaMemcpy(d_dir.p, dir, 3 * (size_t)nrays * sizeof(double), cudaMemcpyHostToDevice));
+    rt::RayBatchArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.sc = scene_dev(sc, mode); a.org = d_org.p; a.dir = d_dir.p; a.nrays = nrays; a.tmin = tmin; a.tmax = tmax;
+    a.scan_mode = mode; a.idx_out = d_idx.p; a.rec_out = d_rec.p;
+    rc = run_hit_kernel(sc, 0, a, nrays);
+    if (rc) return rc;
+    RT_CUDA(cudaMemcpy(idx_out, d_idx.p, (size_t)nrays * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    RT_CUDA(cudaMemcpy(rec_out, d_rec.p, 8 * (size_t)nrays * sizeof(double), cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_ray_color(const rt_scene* scene, const double* org, const double* dir, int32_t nrays, int32_t depth, uint64_t seed,
+                 int32_t early_out, int32_t scan_mode, double* rgb_out, rt_stats* st) {
+    if (!scene || !org || !dir || !rgb_out || nrays < 0) return fail(RT_ERR_INVALID, "bad argument");
+    if (st) std::memset(st, 0, sizeof *st);
+    if (nrays == 0) return RT_OK;
+    rt_scene* sc = const_cast<rt_scene*>(scene);
+    DeviceGuard guard(sc->device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    int mode = 0;
+    int rc = resolve_scan_mode(sc, scan_mode, &mode);
+    if (rc) return rc;
+    DevBuf<double> d_org, d_dir, d_rgb;
+    RT_CUDA(d_org.alloc(3 * (size_t)nrays)); RT_CUDA(d_dir.alloc(3 * (size_t)nrays)); RT_CUDA(d_rgb.alloc(3 * (size_t)nrays));
+    RT_CUDA(cudaMemcpy(d_org.p, org, 3 * (size_t)nrays * sizeof(double), cudaMemcpyHostToDevice));
+    RT_CUDA(cudaMemcpy(d_dir.p, dir, 3 * (size_t)nrays * sizeof(double), cudaMemcpyHostToDevice));
+    RT_CUDA(cudaMemset(sc->d_stats, 0, rt::kNumStats * sizeof(unsigned long long)));
+    rt::RayBatchArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.sc = scene_dev(sc, mode); a.org = d_org.p; a.dir = d_dir.p; a.nrays = nrays; a.scan_mode = mode;
+    a.depth = depth; a.early_out = early_out; a.key0 = (uint32_t)seed; a.key1 = (uint32_t)(seed >> 32);
+    a.rgb_out = d_rgb.p; a.stats = sc->d_stats;
+    const rt::SmemLayout S = rt::smem_layout(a.sc.npad, 1);
+    RT_CUDA(cudaFuncSetAttribute(rt::ray_color_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
+    rt::ray_color_kernel<<<batch_grid(sc, nrays), rt::kThreads, S.total>>>(a);
+    RT_CUDA(cudaGetLastError());
+    RT_CUDA(cudaDeviceSynchronize());
+    RT_CUDA(cudaMemcpy(rgb_out, d_rgb.p, 3 * (size_t)nrays * sizeof(double), cudaMemcpyDeviceToHost));
+    if (st) {
+        unsigned long long h[rt::kNumStats];
+        RT_CUDA(cudaMemcpy(h, sc->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+        st->samples = h[rt::ST_SAMPLES]; st->casts = h[rt::ST_CASTS]; st->exact_tests = h[rt::ST_EXACT_TESTS];
+        st->sphere_tests = mode == RT_SCAN_FILTERED ? h[rt::ST_CASTS] * (uint64_t)sc->n : 0;
+        st->black = h[rt::ST_BLACK]; st->early_outs = h[rt::ST_EARLY_OUTS]; st->primary_hits = h[rt::ST_PRIMARY_HITS];
+        st->overflows = h[rt::ST_OVERFLOWS]; st->launches = 1;
+    }
+    return RT_OK;
+}
+
+int rt_write_color(const double* rgb_sum, int32_t npix, int32_t spp, int32_t device, int32_t* out) {
+    if (!rgb_sum || !out || npix < 0 || spp < 1) return fail(RT_ERR_INVALID, "bad argument");
+    if (npix == 0) return RT_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    DevBuf<double> d_in; DevBuf<int32_t> d_out;
+    RT_CUDA(d_in.alloc(3 * (size_t)npix)); RT_CUDA(d_out.alloc(3 * (size_t)npix));
+    RT_CUDA(cudaMemcpy(d_in.p, rgb_sum, 3 * (size_t)npix * sizeof(double), cudaMemcpyHostToDevice));
+    rt::write_color_kernel<<<(npix + 255) / 256 > 1024 ? 1024 : (npix + 255) / 256, 256>>>(d_in.p, npix, spp, d_out.p);
+    RT_CUDA(cudaGetLastError());
+    RT_CUDA(cudaMemcpy(out, d_out.p, 3 * (size_t)npix * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_get_ray(const rt_camera* cam, const double* uv, int32_t nq, int32_t device, double* out) {
+    if (!cam || !uv || !out || nq < 0) return fail(RT_ERR_INVALID, "bad argument");
+    if (nq == 0) return RT_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    DevBuf<double> d_uv, d_out;
+    RT_CUDA(d_uv.alloc(2 * (size_t)nq)); RT_CUDA(d_out.alloc(6 * (size_t)nq));
+    RT_CUDA(cudaMemcpy(d_uv.p, uv, 2 * (size_t)nq * sizeof(double), cudaMemcpyHostToDevice));
+    rt::CamArgs c;
+    for (int e = 0; e < 3; ++e) {
+        c.org[e] = cam->origin[e]; c.llc[e] = cam->lower_left_corner[e]; c.hor[e] = cam->horizontal[e]; c.ver[e] = cam->vertical[e];
+    }
+    rt::get_ray_kernel<<<(nq + 255) / 256 > 1024 ? 1024 : (nq + 255) / 256, 256>>>(c, d_uv.p, nq, d_out.p);
+    RT_CUDA(cudaGetLastError());
+    RT_CUDA(cudaMemcpy(out, d_out.p, 6 * (size_t)nq * sizeof(double), cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_philox(const uint32_t* ctr4, const uint32_t* key2, int32_t nblocks, int32_t device, uint32_t* out4) {
+    if (!ctr4 || !key2 || !out4 || nblocks < 0) return fail(RT_ERR_INVALID, "bad argument");
+    if (nblocks == 0) return RT_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    DevBuf<uint32_t> d_ctr, d_key, d_out;
+    RT_CUDA(d_ctr.alloc(4 * (size_t)nblocks)); RT_CUDA(d_key.alloc(2)); RT_CUDA(d_out.alloc(4 * (size_t)nblocks));
+    RT_CUDA(cudaMemcpy(d_ctr.p, ctr4, 4 * (size_t)nblocks * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    RT_CUDA(cudaMemcpy(d_key.p, key2, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    rt::philox_kernel<<<(nblocks + 255) / 256 > 1024 ? 1024 : (nblocks + 255) / 256, 256>>>(d_ctr.p, d_key.p, nblocks, d_out.p);
+    RT_CUDA(cudaGetLastError());
+    RT_CUDA(cudaMemcpy(out4, d_out.p, 4 * (size_t)nblocks * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_measure_fp32_peak(int32_t device, double* fma_per_s_out, double* ms_out) {
+    if (!fma_per_s_out) return fail(RT_ERR_INVALID, "NULL out");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    RT_CUDA(cudaGetDeviceProperties(&prop, device));
+    DevBuf<float> d_out;
+    RT_CUDA(d_out.alloc(1));
+    cudaEvent_t e0, e1;
+    RT_CUDA(cudaEventCreate(&e0)); RT_CUDA(cudaEventCreate(&e1));
+    const int grid = prop.multiProcessorCount * 8, iters = 4096;
+    const double fmas = (double)grid * 256.0 * (double)iters * 16.0 * 8.0;
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 4; ++rep) {
+        RT_CUDA(cudaEventRecord(e0));
+        rt::ffma_peak_kernel<<<grid, 256>>>(d_out.p, iters, 1.0000001f, 1e-9f);
+        RT_CUDA(cudaEventRecord(e1));
+        RT_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        RT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *fma_per_s_out = fmas / (best_ms * 1e-3);
+    if (ms_out) *ms_out = best_ms;
+    return RT_OK;
+}
+
+}  // extern "C"

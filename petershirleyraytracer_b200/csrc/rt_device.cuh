@@ -1,0 +1,319 @@
+// rt_device.cuh -- device-side building blocks of the sm_100a path-tracing hot path.
+//
+// Reference semantics (fengye/PeterShirleyRaytracer, cited as programs/<file>:<line>) are reproduced
+// EXACTLY: every quantity that feeds a decision or the image is computed in FP64 with one rounding per
+// operation in the reference's evaluation order (__dmul_rn/__dadd_rn/... never contract into FMA).
+// What makes it fast is that the O(N) part of hittable_list::hit (programs/hittable_list.cc:9-17) is a
+// *conservative FP32 cull*: 8 FP32-pipe instructions per (ray, sphere) decide "cannot be hit" with a
+// rigorous error bound; only the few survivors run the FP64 sphere::hit (programs/sphere.cc:3-40), in
+// list order with the shrinking tmax, so index / t / p / normal are bit-identical to the reference.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rt {
+
+// ---------------------------------------------------------------- constants
+constexpr int kTileW = 8, kTileH = 8, kTilePix = kTileW * kTileH;  // one warp renders one tile at a time
+constexpr int kThreads = 256;                                       // 8 warps per CTA
+constexpr int kWarps = kThreads / 32;
+constexpr int kCandCap = 12;        // survivors per cast kept in smem; more -> full FP64 scan for that cast
+constexpr int kScanUnroll = 4;      // spheres per scan step (one LDS.128 each)
+constexpr int kMaxLinear = 4096;    // cull entries resident in shared memory (64 KB)
+constexpr int kFixShift = 44;       // radiance accumulates as 20.44 fixed point (order-independent sums)
+constexpr int kNumStats = 10;
+
+enum StatSlot { ST_SAMPLES = 0, ST_CASTS, ST_SPHERE_TESTS, ST_NODE_TESTS, ST_EXACT_TESTS, ST_BLACK, ST_EARLY_OUTS,
+                ST_PRIMARY_HITS, ST_OVERFLOWS, ST_UNUSED };
+
+// error-bound constants of the FP32 cull (see DESIGN.md "cull error bound"):
+// |D_fp32 - D| <= 2^-24 * (17 (|c|+|o|)^2 + 6 r^2) <= 2^-24 * (34 |c|^2 + 34 |o|^2 + 6 r^2); we fold
+// 2^-24 * (40 |c|^2 + 8 r^2) into the per-sphere constant and 2^-24 * 40 |o|^2 into the per-ray constant.
+constexpr double kCullEps = 5.9604644775390625e-08;  // 2^-24
+constexpr double kCullKc = 40.0, kCullKr = 8.0, kCullKo = 40.0;
+
+// ---------------------------------------------------------------- FP64, reference evaluation order
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
+// programs/vec3.h:156-159: (u0*v0 + u1*v1) + u2*v2
+__device__ __forceinline__ double ddot(double ax, double ay, double az, double bx, double by, double bz) {
+    return dadd(dadd(dmul(ax, bx), dmul(ay, by)), dmul(az, bz));
+}
+
+// ---------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// 32-bit word -> [0,1): exact in double
+__device__ __forceinline__ double u32_unit(uint32_t w) { return dmul((double)w, 1.0 / 4294967296.0); }
+
+// ---------------------------------------------------------------- scene / launch arguments
+struct SceneDev {
+    const float4* filt;    // npad entries {cx, cy, cz, |c|^2 - r^2 - E_k} (FP32 cull), padded with never-pass entries
+    const double4* exact;  // n entries {cx, cy, cz, r} (FP64, list order)
+    int n, npad;
+};
+
+struct RenderArgs {
+    SceneDev sc;
+    double cam_org[3], cam_llc[3], cam_hor[3], cam_ver[3];
+    double tmin;
+    int W, H, spp, max_depth;
+    uint32_t key0, key1;
+    int jitter, early_out, scan_mode;
+    int tiles_x, tiles_total, shard_rank, shard_count, tiles_local;
+    int chunks, chunk_spp, units_local;  // sample chunks per tile; units = tiles_local * chunks
+    int compact_out;
+    uchar4* out;
+    double* sum_out;               // optional W*H*3
+    unsigned int* unit_counter;    // persistent-warp work queue head
+    unsigned long long* accum;     // tiles_local * 192 fixed-point sums (used when chunks > 1)
+    unsigned int* tile_done;       // tiles_local chunk-completion counters
+    unsigned long long* stats;
+};
+
+// ---------------------------------------------------------------- TMA bulk staging of the cull array
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// One thread arms an mbarrier with the byte count and issues cp.async.bulk (TMA, SASS UBLKCP) pieces;
+// every thread then waits on the barrier's phase 0.  bytes is a multiple of 16.
+__device__ __forceinline__ void stage_bulk(void* s_dst, const void* g_src, uint32_t bytes, uint64_t* s_mbar) {
+    const uint32_t mbar = smem_u32(s_mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+        const uint32_t kPiece = 16384;
+        for (uint32_t off = 0; off < bytes; off += kPiece) {
+            const uint32_t sz = (bytes - off < kPiece) ? (bytes - off) : kPiece;
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    smem_u32((const char*)s_dst + off)),
+                "l"((const char*)g_src + off), "r"(sz), "r"(mbar)
+                : "memory");
+        }
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(mbar)
+            : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- the FP32 conservative cull
+struct CullRay {  // per-cast constants, 8 registers
+    float dx, dy, dz;  // unit direction
+    float ndo;         // -(d̂ . o)
+    float mx, my, mz;  // -2 o
+    float o2;          // |o|^2 - E_o, rounded down
+};
+
+// Builds the cull constants of one ray in FP64 and rounds once.  A dead slot gets constants for which no
+// entry can pass (D = -inf).
+__device__ __forceinline__ CullRay make_cull_ray(bool alive, double ox, double oy, double oz, double dx, double dy,
+                                                 double dz, double A) {
+    CullRay f;
+    if (alive) {
+        const double inv = rsqrt(A);
+        const double ux = dx * inv, uy = dy * inv, uz = dz * inv;
+        f.dx = (float)ux; f.dy = (float)uy; f.dz = (float)uz;
+        f.ndo = (float)(-(ux * ox + uy * oy + uz * oz));
+        f.mx = (float)(-2.0 * ox); f.my = (float)(-2.0 * oy); f.mz = (float)(-2.0 * oz);
+        const double g2 = ox * ox + oy * oy + oz * oz;
+        f.o2 = __double2float_rd(g2 - kCullEps * kCullKo * g2);
+    } else {
+        f.dx = f.dy = f.dz = 0.f; f.ndo = 0.f; f.mx = f.my = f.mz = 0.f;
+        f.o2 = __int_as_float(0x7f800000);
+    }
+    return f;
+}
+
+// D = (d̂.(c-o))^2 - (|c-o|^2 - r^2) + E, expanded so that only 8 FP32-pipe instructions remain:
+// 3 FFMA (b) + 1 FADD + 3 FFMA (q) + 1 FFMA (D).  The sphere passes unless D < 0 (NaN passes).
+__device__ __forceinline__ float cull_D(const CullRay& f, const float4 s) {
+    float b = fmaf(f.dz, s.z, f.ndo);
+    b = fmaf(f.dy, s.y, b);
+    b = fmaf(f.dx, s.x, b);
+    float q = s.w + f.o2;
+    q = fmaf(f.mx, s.x, q);
+    q = fmaf(f.my, s.y, q);
+    q = fmaf(f.mz, s.z, q);
+    return fmaf(b, b, -q);
+}
+
+// Scans the npad cull entries in shared memory for R rays at once; survivors (list order) go to the
+// per-slot candidate lists cand[(e*R + r)*stride].  All lanes execute the same instruction stream; the
+// only divergent code is the (rare) append.
+template <int R>
+__device__ __forceinline__ void cull_scan(const float4* __restrict__ s_filt, int npad, const CullRay (&f)[R],
+                                          uint16_t* cand, int stride, int (&cnt)[R], bool (&ovf)[R]) {
+#pragma unroll 1
+    for (int k = 0; k < npad; k += kScanUnroll) {
+        float4 s[kScanUnroll];
+#pragma unroll
+        for (int u = 0; u < kScanUnroll; ++u) s[u] = s_filt[k + u];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float D[kScanUnroll];
+            uint32_t all_neg = 0x80000000u;
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; ++u) {
+                D[u] = cull_D(f[r], s[u]);
+                all_neg &= __float_as_uint(D[u]);
+            }
+            if ((int)all_neg >= 0) {  // at least one sign bit clear: some entry passes (or is NaN)
+#pragma unroll
+                for (int u = 0; u < kScanUnroll; ++u) {
+                    if (!(D[u] < 0.f)) {
+                        if (cnt[r] < kCandCap) {
+                            cand[(cnt[r] * R + r) * stride] = (uint16_t)(k + u);
+                            ++cnt[r];
+                        } else {
+                            ovf[r] = true;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- FP64 exact sphere::hit
+struct Best {
+    double t;  // closest_so_far (programs/hittable_list.cc:7,14)
+    double C;  // value of C (programs/sphere.cc:11) of the kept hit, for the exact early-out
+    int k;     // list index of the kept hit, -1 = none
+};
+
+// programs/sphere.cc:3-32 for sphere k against (o, d) with A = dot(d,d) hoisted, tmax = best.t; on success
+// the caller's record (t, k) is replaced, which is hittable_list.cc:13-15.  The hit record itself
+// (p, normal) is only needed for the final winner and is built by make_record().
+__device__ __forceinline__ void exact_test(const double4* __restrict__ exact, int k, double ox, double oy, double oz,
+                                           double dx, double dy, double dz, double A, double tmin, Best& best) {
+    const double2 c01 = __ldg(reinterpret_cast<const double2*>(exact + k));
+    const double2 c23 = __ldg(reinterpret_cast<const double2*>(exact + k) + 1);
+    const double amx = dsub(ox, c01.x), amy = dsub(oy, c01.y), amz = dsub(oz, c23.x);  // sphere.cc:7
+    const double HALF_B = ddot(dx, dy, dz, amx, amy, amz);                              // sphere.cc:10
+    const double C = dsub(ddot(amx, amy, amz, amx, amy, amz), dmul(c23.y, c23.y));      // sphere.cc:11
+    const double disc = dsub(dmul(HALF_B, HALF_B), dmul(A, C));                         // sphere.cc:14
+    if (disc < 0) return;                                                                // sphere.cc:15-18
+    const double sqrt_d = dsqrt(disc);
+    double t = ddiv(dsub(-HALF_B, sqrt_d), A);  // sphere.cc:24
+    if (t < tmin || t > best.t) {               // sphere.cc:26 (closed interval)
+        t = ddiv(dadd(-HALF_B, sqrt_d), A);     // sphere.cc:29
+        if (t < tmin || t > best.t) return;     // sphere.cc:30-31
+    }
+    best.t = t; best.C = C; best.k = k;
+}
+
+struct Record {  // programs/hittable.h:7-13
+    double px, py, pz, nx, ny, nz;
+    bool front_face;
+};
+
+// programs/sphere.cc:34-36 + programs/hittable.h:14-18 for the kept hit
+__device__ __forceinline__ Record make_record(const double4* __restrict__ exact, const Best& best, double ox, double oy,
+                                              double oz, double dx, double dy, double dz) {
+    const double2 c01 = __ldg(reinterpret_cast<const double2*>(exact + best.k));
+    const double2 c23 = __ldg(reinterpret_cast<const double2*>(exact + best.k) + 1);
+    Record rec;
+    rec.px = dadd(ox, dmul(best.t, dx));  // programs/ray.h:27 orig + t*dir
+    rec.py = dadd(oy, dmul(best.t, dy));
+    rec.pz = dadd(oz, dmul(best.t, dz));
+    const double inv_r = ddiv(1.0, c23.y);  // programs/vec3.h:151-154: (1/t) * v
+    const double wx = dmul(inv_r, dsub(rec.px, c01.x));
+    const double wy = dmul(inv_r, dsub(rec.py, c01.y));
+    const double wz = dmul(inv_r, dsub(rec.pz, c23.x));
+    rec.front_face = ddot(dx, dy, dz, wx, wy, wz) < 0;
+    rec.nx = rec.front_face ? wx : -wx;
+    rec.ny = rec.front_face ? wy : -wy;
+    rec.nz = rec.front_face ? wz : -wz;
+    return rec;
+}
+
+// hittable_list::hit for one ray given its survivors (or the full list when ovf): list order, shrinking tmax.
+__device__ __forceinline__ Best resolve_hits(const SceneDev& sc, bool ovf, int cnt, const uint16_t* cand, int cand_step,
+                                             double ox, double oy, double oz, double dx, double dy, double dz, double A,
+                                             double tmin, double tmax, uint32_t& n_exact) {
+    Best best;
+    best.t = tmax; best.C = 1.0; best.k = -1;
+    if (!ovf) {
+        for (int e = 0; e < cnt; ++e) {
+            const int k = cand[e * cand_step];
+            if (k < sc.n) { exact_test(sc.exact, k, ox, oy, oz, dx, dy, dz, A, tmin, best); ++n_exact; }
+        }
+    } else {
+        for (int k = 0; k < sc.n; ++k) exact_test(sc.exact, k, ox, oy, oz, dx, dy, dz, A, tmin, best);
+        n_exact += (uint32_t)sc.n;
+    }
+    return best;
+}
+
+// programs/vec3.h:83-109 random_in_hemisphere driven by Philox blocks (one block per rejection try)
+__device__ __forceinline__ void random_in_hemisphere(uint32_t pix, uint32_t smp, uint32_t& blk, uint32_t k0, uint32_t k1,
+                                                     double nx, double ny, double nz, double& rx, double& ry,
+                                                     double& rz) {
+    for (;;) {
+        const uint4 w = philox4x32_10(pix, smp, blk, 0u, k0, k1);
+        ++blk;
+        // programs/random.h:10-14: min + (max-min)*xi with (min,max) = (-1,1)
+        rx = dadd(-1.0, dmul(2.0, u32_unit(w.x)));
+        ry = dadd(-1.0, dmul(2.0, u32_unit(w.y)));
+        rz = dadd(-1.0, dmul(2.0, u32_unit(w.z)));
+        const double l2 = dadd(dadd(dmul(rx, rx), dmul(ry, ry)), dmul(rz, rz));  // programs/vec3.h:63-66
+        if (!(l2 > 1.0)) break;                                                  // programs/vec3.h:90
+    }
+    if (!(ddot(rx, ry, rz, nx, ny, nz) > 0)) { rx = -rx; ry = -ry; rz = -rz; }  // programs/vec3.h:105-108
+}
+
+// programs/main.cc:46-48 sky colour of a ray that missed, times att = 0.5^bounces
+__device__ __forceinline__ void sky_color(double dx, double dy, double dz, double A, int bounces, double& r, double& g,
+                                          double& b) {
+    const double inv_len = ddiv(1.0, dsqrt(A));  // unit_vector = v / v.length() = (1/len) * v
+    const double uy = dmul(inv_len, dy);
+    const double t = dmul(0.5, dadd(uy, 1.0));
+    const double omt = dsub(1.0, t);
+    const double att = __longlong_as_double((long long)(1023 - bounces) << 52);  // 0.5^bounces, exact
+    r = dmul(att, dadd(dmul(omt, 1.0), dmul(t, 0.5)));
+    g = dmul(att, dadd(dmul(omt, 1.0), dmul(t, 0.7)));
+    b = dmul(att, dadd(dmul(omt, 1.0), dmul(t, 1.0)));
+    (void)dx; (void)dz;
+}
+
+// programs/color.h:16-23 for one channel
+__device__ __forceinline__ int write_color_channel(double sum, double one_over_samples) {
+    double x = dsqrt(dmul(sum, one_over_samples));
+    x = (x < 0.0) ? 0.0 : x;        // std::max(x, 0.0)
+    x = (0.999 < x) ? 0.999 : x;    // std::min(., 0.999)
+    return (int)dmul(255.999, x);
+}
+
+// programs/camera.h:25-28
+__device__ __forceinline__ void camera_ray(const double* org, const double* llc, const double* hor, const double* ver,
+                                           double u, double v, double& dx, double& dy, double& dz) {
+    dx = dsub(dadd(dadd(llc[0], dmul(u, hor[0])), dmul(v, ver[0])), org[0]);
+    dy = dsub(dadd(dadd(llc[1], dmul(u, hor[1])), dmul(v, ver[1])), org[1]);
+    dz = dsub(dadd(dadd(llc[2], dmul(u, hor[2])), dmul(v, ver[2])), org[2]);
+}
+
+}  // namespace rt
