@@ -84,32 +84,41 @@ static inline void rng_jitter(rng_t* g, double* xu, double* xv) {
     else { uint32_t w[4]; rng_philox_block(g, w); *xu = u32_to_unit(w[0]); *xv = u32_to_unit(w[1]); }
 }
 
-/* programs/vec3.h:78-81 vec3::random(-1,1) with random_double(min,max) = min + (max-min)*ξ
- * (programs/random.h:10-14).  In RAND15 mode the three calls are evaluated in the order the
- * reference build evaluates them (g++ 13 x86-64: last argument first), which is what makes
- * this file reproduce libref.so bit for bit; in PHILOX mode x,y,z = words 0,1,2 of one block. */
-static inline v3 rng_cube(rng_t* g) {
-    double x, y, z;
-    if (g->mode == ORC_RNG_RAND15) {
-        z = -1.0 + (1.0 - -1.0) * rng_double15(g);
-        y = -1.0 + (1.0 - -1.0) * rng_double15(g);
-        x = -1.0 + (1.0 - -1.0) * rng_double15(g);
-    } else {
-        uint32_t w[4];
-        rng_philox_block(g, w);
-        x = -1.0 + (1.0 - -1.0) * u32_to_unit(w[0]);
-        y = -1.0 + (1.0 - -1.0) * u32_to_unit(w[1]);
-        z = -1.0 + (1.0 - -1.0) * u32_to_unit(w[2]);
-    }
+/* programs/vec3.h:78-81 vec3::random(-1,1) with random_double(min,max) = min + (max-min)*xi
+ * (programs/random.h:10-14), RAND15 mode: the three calls are evaluated in the order the reference build
+ * evaluates them (g++ 13 x86-64: last argument first), which is what makes this file reproduce
+ * libref.so bit for bit. */
+static inline v3 rng_cube15(rng_t* g) {
+    double z = -1.0 + (1.0 - -1.0) * rng_double15(g);
+    double y = -1.0 + (1.0 - -1.0) * rng_double15(g);
+    double x = -1.0 + (1.0 - -1.0) * rng_double15(g);
     return v3_make(x, y, z);
 }
 
-/* programs/vec3.h:83-95: reject only if len² > 1 */
+/* PHILOX mode (shared with the CUDA path, include/rt.h): each block carries two tries of the rejection
+ * loop as six 21-bit uniforms (the reference's rand() has 15 bits): try A = top 21 bits of words 0,1,2;
+ * try B = low 11 bits of words 0,1,2 extended by 10-bit fields of word 3. */
+static inline v3 cube21(uint32_t fx, uint32_t fy, uint32_t fz) {
+    const double s21 = 1.0 / 2097152.0;
+    return v3_make(-1.0 + (1.0 - -1.0) * ((double)fx * s21), -1.0 + (1.0 - -1.0) * ((double)fy * s21),
+                   -1.0 + (1.0 - -1.0) * ((double)fz * s21));
+}
+
+/* programs/vec3.h:83-95: reject only if len^2 > 1 */
 static inline v3 random_in_unit_sphere(rng_t* g) {
     for (;;) {
-        v3 v = rng_cube(g);
-        if (v3_len2(v) > 1.0) continue;
-        return v;
+        if (g->mode == ORC_RNG_RAND15) {
+            v3 v = rng_cube15(g);
+            if (v3_len2(v) > 1.0) continue;
+            return v;
+        }
+        uint32_t w[4];
+        rng_philox_block(g, w);
+        v3 a = cube21(w[0] >> 11, w[1] >> 11, w[2] >> 11);
+        if (!(v3_len2(a) > 1.0)) return a;
+        v3 b = cube21(((w[0] & 0x7ffu) << 10) | (w[3] >> 22), ((w[1] & 0x7ffu) << 10) | ((w[3] >> 12) & 0x3ffu),
+                      ((w[2] & 0x7ffu) << 10) | ((w[3] >> 2) & 0x3ffu));
+        if (!(v3_len2(b) > 1.0)) return b;
     }
 }
 /* programs/vec3.h:102-109: keep if dot > 0, else negate (dot == 0 negates) */

@@ -158,7 +158,7 @@ class Camera:
 
 def make_params(width: int, height: int, spp: int, max_depth: int = 50, seed: int = 0, tmin: float = 0.0,
                 jitter: bool = True, early_out: bool = True, scan_mode: int = SCAN_AUTO, shard_rank: int = 0,
-                shard_count: int = 1, paths_per_lane: int = 0, chunks: int = 0) -> RtParams:
+                shard_count: int = 1, paths_per_lane: int = 0, chunks: int = 0, cull_smem: bool = False) -> RtParams:
     p = RtParams()
     p.width, p.height, p.spp, p.max_depth = width, height, spp, max_depth
     p.seed, p.tmin = seed & 0xFFFFFFFFFFFFFFFF, tmin
@@ -166,6 +166,7 @@ def make_params(width: int, height: int, spp: int, max_depth: int = 50, seed: in
     p.shard_rank, p.shard_count = shard_rank, shard_count
     p.reserved[0] = paths_per_lane  # tuning knob: paths per lane (0 = default)
     p.reserved[1] = chunks          # tuning knob: sample chunks per tile (0 = auto)
+    p.reserved[2] = 1 if cull_smem else 0  # A/B knob: cull array from TMA-staged shared memory instead of the constant bank
     return p
 
 

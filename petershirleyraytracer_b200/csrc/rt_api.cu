@@ -101,7 +101,7 @@ int resolve_scan_mode(const rt_scene* sc, int mode, int* out) {
     if (mode == RT_SCAN_AUTO) mode = RT_SCAN_FILTERED;
     if (mode == RT_SCAN_BVH) return fail(RT_ERR_UNSUPPORTED, "BVH traversal is not built yet");
     if (mode == RT_SCAN_FILTERED && sc->npad > rt::kMaxLinear)
-        return fail(RT_ERR_UNSUPPORTED, "linear cull scan holds at most 4096 spheres in shared memory; use RT_SCAN_EXACT or the BVH");
+        return fail(RT_ERR_UNSUPPORTED, "linear cull scan holds at most 4064 spheres (64 KB constant bank); use RT_SCAN_EXACT or the BVH");
     *out = mode;
     return RT_OK;
 }
@@ -150,9 +150,18 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
 
     int R = p->reserved[0];
     if (R == 0) R = 2;
-    if (R != 1 && R != 2) return fail(RT_ERR_INVALID, "reserved[0] (paths per lane) must be 0, 1 or 2");
-    const rt::SmemLayout S = rt::smem_layout(a.sc.npad, R);
-    auto kern = (R == 1) ? rt::render_kernel<1> : rt::render_kernel<2>;
+    if (R != 1 && R != 2 && R != 4) return fail(RT_ERR_INVALID, "reserved[0] (paths per lane) must be 0, 1, 2 or 4");
+    // cull array source: constant bank (default; FFMAs then read a uniform-register operand) or the
+    // TMA-staged shared-memory copy (reserved[2] == 1), kept for A/B evidence
+    const bool use_const = p->reserved[2] != 1 && mode == RT_SCAN_FILTERED;
+    if (use_const) {
+        RT_CUDA(cudaMemcpyToSymbolAsync(rt::c_filt, sc->d_filt, (size_t)(sc->npad + rt::kScanPad) * sizeof(float4), 0,
+                                        cudaMemcpyDeviceToDevice, stream));
+    }
+    const rt::RenderSmem S = rt::render_smem(use_const ? 0 : a.sc.npad, R);
+    void (*kern)(const rt::RenderArgs) = nullptr;
+    if (use_const) kern = R == 1 ? rt::render_kernel<1, true> : (R == 2 ? rt::render_kernel<2, true> : rt::render_kernel<4, true>);
+    else kern = R == 1 ? rt::render_kernel<1, false> : (R == 2 ? rt::render_kernel<2, false> : rt::render_kernel<4, false>);
     RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
     int per_sm = 0;
     RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, rt::kThreads, S.total));
@@ -248,15 +257,15 @@ int rt_upload_scene(const double* centres_xyz, const double* radii, int32_t n, i
     rt_scene* sc = new (std::nothrow) rt_scene();
     if (!sc) return fail(RT_ERR_NOMEM, "host allocation failed");
     sc->device = device; sc->n = n;
-    sc->npad = (n + rt::kScanUnroll - 1) / rt::kScanUnroll * rt::kScanUnroll;
+    sc->npad = (n + rt::kScanPad - 1) / rt::kScanPad * rt::kScanPad;  // the arrays carry kScanPad more never-pass entries
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete sc; return fail(RT_ERR_CUDA, "cudaGetDeviceProperties failed"); }
     sc->sm_count = prop.multiProcessorCount;
 
     // FP32 cull entries {c, |c|^2 - r^2 - E_k}: computed in FP64, constant term rounded DOWN.
-    std::vector<float4> filt((size_t)sc->npad > 0 ? sc->npad : 1);
+    std::vector<float4> filt((size_t)sc->npad + rt::kScanPad);
     std::vector<double4> exact((size_t)n > 0 ? n : 1);
-    for (int k = 0; k < sc->npad; ++k) {
+    for (int k = 0; k < sc->npad + rt::kScanPad; ++k) {
         float4 f;
         if (k < n) {
             const double cx = centres_xyz[3 * k], cy = centres_xyz[3 * k + 1], cz = centres_xyz[3 * k + 2], r = radii[k];
@@ -373,7 +382,7 @@ int rt_deinterleave(const rt_params* p, const void* d_gathered, void* d_rgba, in
 }
 
 static int run_hit_kernel(rt_scene* sc, int mode_kernel, rt::RayBatchArgs& a, int nrays) {
-    const rt::SmemLayout S = rt::smem_layout(a.sc.npad, 1);
+    const rt::BatchSmem S = rt::batch_smem(a.sc.npad);
     auto kern = mode_kernel == 0 ? rt::hit_kernel<0> : rt::hit_kernel<1>;
     RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
     kern<<<batch_grid(sc, nrays), rt::kThreads, S.total>>>(a);
@@ -457,7 +466,7 @@ int rt_ray_color(const rt_scene* scene, const double* org, const double* dir, in
     a.sc = scene_dev(sc, mode); a.org = d_org.p; a.dir = d_dir.p; a.nrays = nrays; a.scan_mode = mode;
     a.depth = depth; a.early_out = early_out; a.key0 = (uint32_t)seed; a.key1 = (uint32_t)(seed >> 32);
     a.rgb_out = d_rgb.p; a.stats = sc->d_stats;
-    const rt::SmemLayout S = rt::smem_layout(a.sc.npad, 1);
+    const rt::BatchSmem S = rt::batch_smem(a.sc.npad);
     RT_CUDA(cudaFuncSetAttribute(rt::ray_color_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
     rt::ray_color_kernel<<<batch_grid(sc, nrays), rt::kThreads, S.total>>>(a);
     RT_CUDA(cudaGetLastError());

@@ -16,11 +16,11 @@ namespace rt {
 
 // ---------------------------------------------------------------- constants
 constexpr int kTileW = 8, kTileH = 8, kTilePix = kTileW * kTileH;  // one warp renders one tile at a time
-constexpr int kThreads = 256;                                       // 8 warps per CTA
+constexpr int kThreads = 128;                                       // 4 warps per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kCandCap = 12;        // survivors per cast kept in smem; more -> full FP64 scan for that cast
-constexpr int kScanUnroll = 4;      // spheres per scan step (one LDS.128 each)
-constexpr int kMaxLinear = 4096;    // cull entries resident in shared memory (64 KB)
+constexpr int kScanPad = 8;         // cull arrays are padded to a multiple of this, plus one extra group (prefetch)
+constexpr int kMaxLinear = 4064;    // cull entries that fit the 64 KB constant bank (with the prefetch pad)
 constexpr int kFixShift = 44;       // radiance accumulates as 20.44 fixed point (order-independent sums)
 constexpr int kNumStats = 10;
 
@@ -39,6 +39,13 @@ __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a,
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 __device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
+// num / A for the hit distance (programs/sphere.cc:24,29).  With tmin = 0 about half of all hits are
+// self-hits whose numerator is exactly +-0; IEEE gives +-0 / A = +-0 for finite A > 0,
+// so that case is answered directly instead of through the division's special-operand subroutine.
+__device__ __forceinline__ double ddiv_t(double num, double A) {
+    if (num == 0.0 && A > 0.0 && A < __longlong_as_double(0x7ff0000000000000ll)) return num;
+    return __ddiv_rn(num, A);
+}
 // programs/vec3.h:156-159: (u0*v0 + u1*v1) + u2*v2
 __device__ __forceinline__ double ddot(double ax, double ay, double az, double bx, double by, double bz) {
     return dadd(dadd(dmul(ax, bx), dmul(ay, by)), dmul(az, bz));
@@ -121,6 +128,14 @@ __device__ __forceinline__ void stage_bulk(void* s_dst, const void* g_src, uint3
 }
 
 // ---------------------------------------------------------------- the FP32 conservative cull
+// Cull entries live in the constant bank: a warp-uniform index makes the loads ULDC/LDCU into UNIFORM
+// registers, so every FFMA of the scan reads two vector registers + one uniform register.  Measured on
+// B200 (tools/microbench.cu): FFMA with three distinct vector-register sources sustains 22.8 T FMA/s,
+// with a uniform/constant operand 36.2 T FMA/s; the scan costs 11.8 issue slots per test from the
+// constant bank against 13.7 from shared memory (LDS.128 + three-register FFMAs).  The shared-memory
+// variant (TMA-staged) is kept selectable for comparison and for scenes beyond the 64 KB bank.
+__constant__ float4 c_filt[kMaxLinear + kScanPad];
+
 struct CullRay {  // per-cast constants, 8 registers
     float dx, dy, dz;  // unit direction
     float ndo;         // -(d̂ . o)
@@ -161,32 +176,42 @@ __device__ __forceinline__ float cull_D(const CullRay& f, const float4 s) {
     return fmaf(b, b, -q);
 }
 
-// Scans the npad cull entries in shared memory for R rays at once; survivors (list order) go to the
+// Scans the npad cull entries (kConst: constant bank, else shared memory) for R rays at once, U entries per
+// step, software-pipelined: the loads of step i+1 are issued before the arithmetic of step i (the arrays
+// carry one extra never-pass group so the last prefetch stays in bounds).  Survivors (list order) go to the
 // per-slot candidate lists cand[(e*R + r)*stride].  All lanes execute the same instruction stream; the
 // only divergent code is the (rare) append.
-template <int R>
+template <int R, int U, bool kConst>
 __device__ __forceinline__ void cull_scan(const float4* __restrict__ s_filt, int npad, const CullRay (&f)[R],
                                           uint16_t* cand, int stride, int (&cnt)[R], bool (&ovf)[R]) {
-#pragma unroll 1
-    for (int k = 0; k < npad; k += kScanUnroll) {
-        float4 s[kScanUnroll];
+    // kv mirrors k in a VECTOR register (opaque to the compiler).  If the stored index were derived from
+    // k itself, ptxas would move the loop counter off the uniform datapath and load every cull entry into
+    // vector registers (LDC instead of LDCU): three-register FFMAs at 63% rate instead of FFMA R,UR,R.
+    int kv;
+    asm volatile("mov.u32 %0, 0;" : "=r"(kv));
+    float4 s[U];
 #pragma unroll
-        for (int u = 0; u < kScanUnroll; ++u) s[u] = s_filt[k + u];
+    for (int u = 0; u < U; ++u) s[u] = kConst ? c_filt[u] : s_filt[u];
+#pragma unroll 2
+    for (int k = 0; k < npad; k += U, kv += U) {
+        float4 nx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) nx[u] = kConst ? c_filt[k + U + u] : s_filt[k + U + u];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            float D[kScanUnroll];
+            float D[U];
             uint32_t all_neg = 0x80000000u;
 #pragma unroll
-            for (int u = 0; u < kScanUnroll; ++u) {
+            for (int u = 0; u < U; ++u) {
                 D[u] = cull_D(f[r], s[u]);
                 all_neg &= __float_as_uint(D[u]);
             }
             if ((int)all_neg >= 0) {  // at least one sign bit clear: some entry passes (or is NaN)
 #pragma unroll
-                for (int u = 0; u < kScanUnroll; ++u) {
+                for (int u = 0; u < U; ++u) {
                     if (!(D[u] < 0.f)) {
                         if (cnt[r] < kCandCap) {
-                            cand[(cnt[r] * R + r) * stride] = (uint16_t)(k + u);
+                            cand[(cnt[r] * R + r) * stride] = (uint16_t)(kv + u);
                             ++cnt[r];
                         } else {
                             ovf[r] = true;
@@ -195,6 +220,8 @@ __device__ __forceinline__ void cull_scan(const float4* __restrict__ s_filt, int
                 }
             }
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u) s[u] = nx[u];
     }
 }
 
@@ -218,9 +245,9 @@ __device__ __forceinline__ void exact_test(const double4* __restrict__ exact, in
     const double disc = dsub(dmul(HALF_B, HALF_B), dmul(A, C));                         // sphere.cc:14
     if (disc < 0) return;                                                                // sphere.cc:15-18
     const double sqrt_d = dsqrt(disc);
-    double t = ddiv(dsub(-HALF_B, sqrt_d), A);  // sphere.cc:24
+    double t = ddiv_t(dsub(-HALF_B, sqrt_d), A);  // sphere.cc:24
     if (t < tmin || t > best.t) {               // sphere.cc:26 (closed interval)
-        t = ddiv(dadd(-HALF_B, sqrt_d), A);     // sphere.cc:29
+        t = ddiv_t(dadd(-HALF_B, sqrt_d), A);   // sphere.cc:29
         if (t < tmin || t > best.t) return;     // sphere.cc:30-31
     }
     best.t = t; best.C = C; best.k = k;
@@ -257,31 +284,40 @@ __device__ __forceinline__ Best resolve_hits(const SceneDev& sc, bool ovf, int c
                                              double tmin, double tmax, uint32_t& n_exact) {
     Best best;
     best.t = tmax; best.C = 1.0; best.k = -1;
-    if (!ovf) {
-        for (int e = 0; e < cnt; ++e) {
-            const int k = cand[e * cand_step];
-            if (k < sc.n) { exact_test(sc.exact, k, ox, oy, oz, dx, dy, dz, A, tmin, best); ++n_exact; }
-        }
-    } else {
-        for (int k = 0; k < sc.n; ++k) exact_test(sc.exact, k, ox, oy, oz, dx, dy, dz, A, tmin, best);
-        n_exact += (uint32_t)sc.n;
+    const int n_iter = ovf ? sc.n : cnt;  // candidate list, or every sphere when the list overflowed
+#pragma unroll 1
+    for (int e = 0; e < n_iter; ++e) {
+        const int k = ovf ? e : (int)cand[e * cand_step];
+        if (k < sc.n) exact_test(sc.exact, k, ox, oy, oz, dx, dy, dz, A, tmin, best);
     }
+    n_exact += (uint32_t)n_iter;
     return best;
 }
 
-// programs/vec3.h:83-109 random_in_hemisphere driven by Philox blocks (one block per rejection try)
+// One rejection try of programs/vec3.h:87-94 from three 21-bit uniforms: v = -1 + 2*xi (random.h:10-14) is
+// exact, and so is the length test.  Returns true if the point is kept (len^2 <= 1, vec3.h:90).
+__device__ __forceinline__ bool cube_try(uint32_t fx, uint32_t fy, uint32_t fz, double& rx, double& ry, double& rz) {
+    const double s21 = 1.0 / 2097152.0;
+    rx = dadd(-1.0, dmul(2.0, dmul((double)fx, s21)));
+    ry = dadd(-1.0, dmul(2.0, dmul((double)fy, s21)));
+    rz = dadd(-1.0, dmul(2.0, dmul((double)fz, s21)));
+    const double l2 = dadd(dadd(dmul(rx, rx), dmul(ry, ry)), dmul(rz, rz));  // programs/vec3.h:63-66
+    return !(l2 > 1.0);
+}
+
+// programs/vec3.h:83-109 random_in_hemisphere driven by Philox blocks.  Every block carries TWO tries of
+// the rejection loop as six 21-bit uniforms (the reference's rand() has 15 bits): try A = top 21 bits of
+// words 0,1,2; try B = the low 11 bits of words 0,1,2 extended by 10-bit fields of word 3.
 __device__ __forceinline__ void random_in_hemisphere(uint32_t pix, uint32_t smp, uint32_t& blk, uint32_t k0, uint32_t k1,
                                                      double nx, double ny, double nz, double& rx, double& ry,
                                                      double& rz) {
     for (;;) {
         const uint4 w = philox4x32_10(pix, smp, blk, 0u, k0, k1);
         ++blk;
-        // programs/random.h:10-14: min + (max-min)*xi with (min,max) = (-1,1)
-        rx = dadd(-1.0, dmul(2.0, u32_unit(w.x)));
-        ry = dadd(-1.0, dmul(2.0, u32_unit(w.y)));
-        rz = dadd(-1.0, dmul(2.0, u32_unit(w.z)));
-        const double l2 = dadd(dadd(dmul(rx, rx), dmul(ry, ry)), dmul(rz, rz));  // programs/vec3.h:63-66
-        if (!(l2 > 1.0)) break;                                                  // programs/vec3.h:90
+        if (cube_try(w.x >> 11, w.y >> 11, w.z >> 11, rx, ry, rz)) break;
+        if (cube_try(((w.x & 0x7ffu) << 10) | (w.w >> 22), ((w.y & 0x7ffu) << 10) | ((w.w >> 12) & 0x3ffu),
+                     ((w.z & 0x7ffu) << 10) | ((w.w >> 2) & 0x3ffu), rx, ry, rz))
+            break;
     }
     if (!(ddot(rx, ry, rz, nx, ny, nz) > 0)) { rx = -rx; ry = -ry; rz = -rz; }  // programs/vec3.h:105-108
 }

@@ -1,14 +1,16 @@
 // rt_kernels.cuh -- the sm_100a kernels of the hot path.
 //
-//   render_kernel<R>   persistent CTAs; each WARP pulls 8x8-pixel tiles from a global counter and owns its
-//                      tile until every sample of it is traced.  Lanes hold R independent paths each and
-//                      re-arm a finished path with the tile's next (pixel, sample) immediately (path
-//                      regeneration), so the bimodal path length of the reference (1-4 casts or 51) does
-//                      not idle lanes.  Per cast: FP32 cull scan of the sphere array in shared memory
-//                      (staged once per CTA by TMA bulk copy), FP64 exact tests of the survivors, FP64
-//                      shading.  Radiance is summed in 20.44 fixed point with shared-memory atomics so the
-//                      image does not depend on scheduling or GPU count; write_color's arithmetic
-//                      (programs/color.h:16-23) runs in FP64 and stores coalesced uchar4.
+//   render_kernel<R>   persistent CTAs of 4 warps; each WARP pulls work units (8x8-pixel tile x sample
+//                      chunk) from a global counter.  Lanes hold R independent paths each and re-arm a
+//                      finished path with the unit's next (pixel, sample) immediately (path regeneration),
+//                      so the bimodal path length of the reference (1-4 casts or 51) does not idle lanes; two
+//                      units overlap per warp so there is no per-unit tail.  Per cast: FP32 cull scan of
+//                      the sphere array (constant bank -> uniform registers, or TMA-staged shared memory),
+//                      FP64 exact tests of the survivors, FP64 shading.  Path state lives in shared memory
+//                      so the FP64 code exists once.  Radiance is summed in 20.44 fixed point (shared-memory
+//                      atomics per warp, global integer atomics across chunks) so the image does not depend
+//                      on scheduling or GPU count; write_color's arithmetic (programs/color.h:16-23) runs in
+//                      FP64 and stores coalesced uchar4.
 //   primary_kernel, hit_kernel, ray_color_kernel   the same device functions behind the per-function
 //                      entry points of include/rt.h (one thread per ray, R = 1).
 #pragma once
@@ -17,18 +19,35 @@
 
 namespace rt {
 
-struct SmemLayout {
-    // [0, filt_bytes)                      float4 cull entries
-    // [filt_bytes, +kWarps*2*kTilePix*3*8) per-warp radiance accumulators (2 buffers of u64)
-    // [.., + kCandCap*R*kThreads*2)        candidate lists (u16)
-    uint32_t filt_bytes, acc_off, cand_off, total;
+// Shared-memory carve-up of the render kernel (R paths per lane).  Everything a path carries between casts
+// lives here, so the FP64 code exists once (a rolled loop over the lane's slots) and the registers of the
+// scan hold only the cull constants.
+struct RenderSmem {
+    // filt   : (npad + kScanPad) float4 cull entries        (shared-memory variant only; TMA bulk copy)
+    // acc    : kWarps * 2 * kTilePix*3 u64                   per-warp radiance accumulators, two units in flight
+    // state  : 6 * R * kThreads double                       ox,oy,oz,dx,dy,dz   [c][r][tid]
+    // meta   : R * kThreads uint4                            pixel id, sample, next Philox block, depth | pixel-in-tile<<16
+    // cand   : kCandCap * R * kThreads u16                   survivors of the cull scan  [e][r][tid]
+    uint32_t filt_bytes, acc_off, state_off, meta_off, cand_off, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int npad, int R) {
-    SmemLayout L;
-    L.filt_bytes = (uint32_t)npad * 16u;
+__host__ __device__ inline RenderSmem render_smem(int npad_smem, int R) {
+    RenderSmem L;
+    L.filt_bytes = npad_smem > 0 ? (uint32_t)(npad_smem + kScanPad) * 16u : 0u;
     L.acc_off = (L.filt_bytes + 127u) & ~127u;
-    L.cand_off = L.acc_off + kWarps * 2 * kTilePix * 3 * 8;
+    L.state_off = L.acc_off + kWarps * 2 * kTilePix * 3 * 8;
+    L.meta_off = L.state_off + 6 * R * kThreads * 8;
+    L.cand_off = L.meta_off + R * kThreads * 16;
     L.total = L.cand_off + kCandCap * R * kThreads * 2;
+    return L;
+}
+
+// per-function kernels (one ray per thread): cull entries + candidate lists
+struct BatchSmem { uint32_t filt_bytes, cand_off, total; };
+__host__ __device__ inline BatchSmem batch_smem(int npad) {
+    BatchSmem L;
+    L.filt_bytes = npad > 0 ? (uint32_t)(npad + kScanPad) * 16u : 0u;
+    L.cand_off = (L.filt_bytes + 127u) & ~127u;
+    L.total = L.cand_off + kCandCap * kThreads * 2;
     return L;
 }
 
@@ -59,7 +78,9 @@ __device__ __forceinline__ void finalize_tile(const RenderArgs& a, int tile_l, c
     const TileGeom g = tile_geom(a, tile_l);
     const double one_over_samples = ddiv(1.0, (double)a.spp);  // programs/color.h:16
     const double inv_fs = 1.0 / (double)(1ull << kFixShift);
-    for (int p = lane; p < kTilePix; p += 32) {
+#pragma unroll 1
+    for (int pj = 0; pj < kTilePix / 32; ++pj) {  // uniform trip count (lane-strided bounds would mark the warp divergent)
+        const int p = pj * 32 + lane;
         const int ly = p / kTileW, lx = p - ly * kTileW;
         if (lx >= g.tw || ly >= g.th) continue;
         unsigned long long v0, v1, v2;
@@ -84,54 +105,60 @@ __device__ __forceinline__ void finalize_tile(const RenderArgs& a, int tile_l, c
 // the warp finalizes straight from shared memory; otherwise sums go to the global integer accumulator
 // (order-independent) and the warp that completes the tile's last chunk finalizes it.
 __device__ __forceinline__ void flush_unit(const RenderArgs& a, const Unit& u, unsigned long long* accp, int lane) {
-    __syncwarp();
+    // No __syncwarp() in here: a warp barrier inside this conditionally executed region makes ptxas treat
+    // the main loop as divergent and drop the scan's uniform-datapath loads.  Ordering against the lanes'
+    // shared-memory atomics comes from the unconditional __syncwarp()s of the main loop.
     if (a.chunks == 1) {
         finalize_tile<false>(a, u.tile_l, accp, lane);
     } else {
         unsigned long long* g = a.accum + (size_t)u.tile_l * (kTilePix * 3);
-        for (int i = lane; i < kTilePix * 3; i += 32) {
-            const unsigned long long v = accp[i];
-            if (v) atomicAdd(g + i, v);
+#pragma unroll
+        for (int j = 0; j < kTilePix * 3 / 32; ++j) {
+            const unsigned long long v = accp[j * 32 + lane];
+            if (v) atomicAdd(g + j * 32 + lane, v);
         }
-        __threadfence();
-        __syncwarp();
+        __threadfence();  // this lane's sums are visible before lane 0 (below, after the vote) counts the chunk
+        const bool all_here = __all_sync(0xffffffffu, true);
         unsigned int d = 0;
-        if (lane == 0) d = atomicAdd(a.tile_done + u.tile_l, 1u);
+        if (lane == 0 && all_here) d = atomicAdd(a.tile_done + u.tile_l, 1u);
         d = __shfl_sync(0xffffffffu, d, 0);
         if (d == (unsigned)a.chunks - 1u) {
             __threadfence();
             finalize_tile<true>(a, u.tile_l, g, lane);
         }
     }
-    __syncwarp();
-    for (int i = lane; i < kTilePix * 3; i += 32) accp[i] = 0ull;
-    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kTilePix * 3 / 32; ++j) accp[j * 32 + lane] = 0ull;
 }
 
 template <int R>
-__global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_constant__ RenderArgs a) {
+struct RenderTraits {
+    static constexpr int kMinBlocks = R >= 4 ? 3 : (R == 2 ? 4 : 6);  // CTAs of 128 threads per SM (smem / register budget)
+    static constexpr int kU = 4;  // cull entries per scan step (x2 in flight: 32 uniform registers of 63)
+};
+
+template <int R, bool kConst>
+__global__ void __launch_bounds__(kThreads, RenderTraits<R>::kMinBlocks) render_kernel(const __grid_constant__ RenderArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t s_mbar;
-    const SmemLayout L = smem_layout(a.sc.npad, R);
+    const RenderSmem L = render_smem(kConst ? 0 : a.sc.npad, R);
     const float4* s_filt = reinterpret_cast<const float4*>(smem);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // two accumulator buffers per warp: the next unit starts while the last paths of the previous one finish
     unsigned long long* acc = reinterpret_cast<unsigned long long*>(smem + L.acc_off) + warp * (2 * kTilePix * 3);
-    uint16_t* cand = reinterpret_cast<uint16_t*>(smem + L.cand_off) + threadIdx.x;
+    double* st = reinterpret_cast<double*>(smem + L.state_off) + tid;      // component c of slot r: st[(c*R + r)*kThreads]
+    uint4* meta = reinterpret_cast<uint4*>(smem + L.meta_off) + tid;       // slot r: meta[r*kThreads]
+    uint16_t* cand = reinterpret_cast<uint16_t*>(smem + L.cand_off) + tid;  // entry e of slot r: cand[(e*R + r)*kThreads]
 
-    for (int i = lane; i < 2 * kTilePix * 3; i += 32) acc[i] = 0ull;
-    stage_bulk(smem, a.sc.filt, L.filt_bytes, &s_mbar);
+#pragma unroll
+    for (int j = 0; j < 2 * kTilePix * 3 / 32; ++j) acc[j * 32 + lane] = 0ull;
+    if (!kConst) stage_bulk(smem, a.sc.filt, L.filt_bytes, &s_mbar);
 
     const double wm1 = (double)(a.W - 1), hm1 = (double)(a.H - 1);
     const double kInf = __longlong_as_double(0x7ff0000000000000ll);
 
-    // per-lane path slots
-    double ox[R], oy[R], oz[R], dx[R], dy[R], dz[R];
-    int depth[R], bounces[R], lpix[R];  // lpix: bits 0-5 pixel in tile, bit 6 accumulator buffer
-    uint32_t pixid[R], smp[R], blk[R];
-    bool alive[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) { alive[r] = false; lpix[r] = 0; }
+    uint32_t alive_mask = 0, par_mask = 0;  // per lane, bit r: slot r holds a live path / its unit is buffer 1
+    uint32_t cntpack = 0;                   // per slot 8 bits: survivors of the last scan (bit 7: list overflowed)
     uint32_t n_samples = 0, n_casts = 0, n_exact = 0, n_black = 0, n_early = 0, n_primary = 0, n_ovf = 0;
 
     Unit u0, u1;
@@ -140,32 +167,84 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
     bool no_more = false;
 
     for (;;) {
+        __syncwarp();  // orders last round's shared-memory atomics before the sums are read below
         // ---------------- retire units whose samples are all traced
         {
-            bool in0 = false, in1 = false;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                in0 |= alive[r] && !(lpix[r] & 64);
-                in1 |= alive[r] && (lpix[r] & 64);
-            }
-            if (u0.valid && u0.next >= u0.total && !__any_sync(0xffffffffu, in0)) { flush_unit(a, u0, acc, lane); u0.valid = 0; }
-            if (u1.valid && u1.next >= u1.total && !__any_sync(0xffffffffu, in1)) { flush_unit(a, u1, acc + kTilePix * 3, lane); u1.valid = 0; }
+            const bool in0 = (alive_mask & ~par_mask) != 0, in1 = (alive_mask & par_mask) != 0;
+            if (__all_sync(0xffffffffu, u0.valid && u0.next >= u0.total && !in0)) { flush_unit(a, u0, acc, lane); u0.valid = 0; }
+            if (__all_sync(0xffffffffu, u1.valid && u1.next >= u1.total && !in1)) { flush_unit(a, u1, acc + kTilePix * 3, lane); u1.valid = 0; }
         }
-        // ---------------- re-arm finished paths with the next (pixel, sample) ids, pulling units as needed
-        bool any_alive = false;
-#pragma unroll
+
+        // ---------------- advance every slot: finish the cast scanned last round, then re-arm dead slots
+#pragma unroll 1
         for (int r = 0; r < R; ++r) {
-            unsigned need = __ballot_sync(0xffffffffu, !alive[r]);
+            const uint32_t bit = 1u << r;
+            if (alive_mask & bit) {
+                const double ox = st[(0 * R + r) * kThreads], oy = st[(1 * R + r) * kThreads], oz = st[(2 * R + r) * kThreads];
+                const double dx = st[(3 * R + r) * kThreads], dy = st[(4 * R + r) * kThreads], dz = st[(5 * R + r) * kThreads];
+                uint4 m = meta[r * kThreads];
+                const int depth = (int)(m.w & 0xffffu), lp = (int)(m.w >> 16);  // lp: bits 0-5 pixel in tile, bit 6 buffer
+                const int bounces = a.max_depth - depth;
+                const double A = ddot(dx, dy, dz, dx, dy, dz);  // programs/sphere.cc:9
+                const int cnt = (int)((cntpack >> (8 * r)) & 0x7fu);
+                const bool ovf = ((cntpack >> (8 * r + 7)) & 1u) != 0;
+                ++n_casts;
+                if (ovf && a.scan_mode == 0) ++n_ovf;
+                const Best best = resolve_hits(a.sc, ovf, cnt, cand + r * kThreads, R * kThreads, ox, oy, oz, dx, dy, dz, A,
+                                               a.tmin, kInf, n_exact);
+                if (best.k < 0) {
+                    // miss: sky (programs/main.cc:46-48) * 0.5^bounces -> fixed-point accumulate
+                    double cr, cg, cb;
+                    sky_color(dx, dy, dz, A, bounces, cr, cg, cb);
+                    const double fs = (double)(1ull << kFixShift);
+                    unsigned long long* ap = acc + ((lp >> 6) * kTilePix + (lp & 63)) * 3;
+                    atomicAdd(ap + 0, __double2ull_rz(cr * fs));
+                    atomicAdd(ap + 1, __double2ull_rz(cg * fs));
+                    atomicAdd(ap + 2, __double2ull_rz(cb * fs));
+                    alive_mask &= ~bit;
+                } else {
+                    if (bounces == 0) ++n_primary;
+                    if (a.early_out && best.t == 0.0 && best.C == 0.0) {
+                        // origin stays on this sphere with C == 0: every later cast hits at t == 0 -> black
+                        ++n_early; ++n_black;
+                        alive_mask &= ~bit;
+                    } else {
+                        const Record rec = make_record(a.sc.exact, best, ox, oy, oz, dx, dy, dz);
+                        double rx, ry, rz;
+                        random_in_hemisphere(m.x, m.y, m.z, a.key0, a.key1, rec.nx, rec.ny, rec.nz, rx, ry, rz);
+                        // programs/main.cc:42-43: target = (p + normal) + rv; next ray = (p, target - p)
+                        const double tgx = dadd(dadd(rec.px, rec.nx), rx);
+                        const double tgy = dadd(dadd(rec.py, rec.ny), ry);
+                        const double tgz = dadd(dadd(rec.pz, rec.nz), rz);
+                        st[(0 * R + r) * kThreads] = rec.px; st[(1 * R + r) * kThreads] = rec.py; st[(2 * R + r) * kThreads] = rec.pz;
+                        st[(3 * R + r) * kThreads] = dsub(tgx, rec.px);
+                        st[(4 * R + r) * kThreads] = dsub(tgy, rec.py);
+                        st[(5 * R + r) * kThreads] = dsub(tgz, rec.pz);
+                        if (depth == 0) {  // programs/main.cc:36-37: the next ray_color call has depth < 0
+                            ++n_black;
+                            alive_mask &= ~bit;
+                        } else {
+                            m.w = (uint32_t)(depth - 1) | ((uint32_t)lp << 16);
+                            meta[r * kThreads] = m;
+                        }
+                    }
+                }
+            }
+
+            // re-arm: hand the next (pixel, sample) ids to dead slots, pulling units as needed
+            unsigned need = __ballot_sync(0xffffffffu, !(alive_mask & bit));
             while (need) {
                 Unit c = cur ? u1 : u0;
-                if (!c.valid || c.next >= c.total) {
+                // (votes make the warp-uniform exits visible to ptxas, which then keeps the scan's loop
+                //  counter and cull entries on the uniform datapath)
+                if (__all_sync(0xffffffffu, !c.valid || c.next >= c.total)) {
                     const int np = c.valid ? (cur ^ 1) : cur;
                     const Unit o = np ? u1 : u0;
-                    if (o.valid || no_more) break;  // other buffer still draining, or frame exhausted
+                    if (__any_sync(0xffffffffu, o.valid || no_more)) break;  // other buffer draining, or frame exhausted
                     unsigned int id = 0;
                     if (lane == 0) id = atomicAdd(a.unit_counter, 1u);
                     id = __shfl_sync(0xffffffffu, id, 0);
-                    if (id >= (unsigned)a.units_local) { no_more = true; break; }
+                    if (__any_sync(0xffffffffu, id >= (unsigned)a.units_local)) { no_more = true; break; }
                     c.valid = 1;
                     c.tile_l = (int)(id / (unsigned)a.chunks);
                     c.chunk = (int)(id - (unsigned)c.tile_l * (unsigned)a.chunks);
@@ -185,92 +264,64 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
                     const uint32_t s = (uint32_t)(c.chunk * a.chunk_spp) + (id - p * ns);
                     const int ly = (int)p / g.tw, lx = (int)p - ly * g.tw;
                     const int i = g.x0 + lx, j = a.H - 1 - (g.y0 + ly);  // j from the bottom (programs/main.cc:72)
-                    lpix[r] = (ly * kTileW + lx) | (cur << 6);
-                    pixid[r] = (uint32_t)(j * a.W + i);
-                    smp[r] = s; blk[r] = 1u;
+                    const uint32_t pixid = (uint32_t)(j * a.W + i);
                     double xu = 0.5, xv = 0.5;
                     if (a.jitter) {
-                        const uint4 w = philox4x32_10(pixid[r], s, 0u, 0u, a.key0, a.key1);
+                        const uint4 w = philox4x32_10(pixid, s, 0u, 0u, a.key0, a.key1);
                         xu = u32_unit(w.x); xv = u32_unit(w.y);
                     }
                     const double u = ddiv(dadd((double)i, xu), wm1);  // programs/main.cc:80
                     const double v = ddiv(dadd((double)j, xv), hm1);  // programs/main.cc:81
-                    ox[r] = a.cam_org[0]; oy[r] = a.cam_org[1]; oz[r] = a.cam_org[2];
-                    camera_ray(a.cam_org, a.cam_llc, a.cam_hor, a.cam_ver, u, v, dx[r], dy[r], dz[r]);
-                    depth[r] = a.max_depth; bounces[r] = 0;
+                    double dx, dy, dz;
+                    camera_ray(a.cam_org, a.cam_llc, a.cam_hor, a.cam_ver, u, v, dx, dy, dz);
                     ++n_samples;
-                    if (a.max_depth >= 0) alive[r] = true;
-                    else ++n_black;  // ray_color(r, world, depth < 0) is black without a cast (main.cc:36)
+                    if (a.max_depth >= 0) {
+                        st[(0 * R + r) * kThreads] = a.cam_org[0]; st[(1 * R + r) * kThreads] = a.cam_org[1];
+                        st[(2 * R + r) * kThreads] = a.cam_org[2];
+                        st[(3 * R + r) * kThreads] = dx; st[(4 * R + r) * kThreads] = dy; st[(5 * R + r) * kThreads] = dz;
+                        meta[r * kThreads] = make_uint4(pixid, s, 1u,
+                                                        (uint32_t)a.max_depth | ((uint32_t)((ly * kTileW + lx) | (cur << 6)) << 16));
+                        alive_mask |= bit;
+                        par_mask = (par_mask & ~bit) | ((uint32_t)cur << r);
+                    } else {
+                        ++n_black;  // ray_color(r, world, depth < 0) is black without a cast (main.cc:36)
+                    }
                 }
                 const unsigned taken = __ballot_sync(0xffffffffu, take);
                 c.next += __popc(taken);
                 need &= ~taken;
                 if (cur) u1 = c; else u0 = c;
-                if (a.max_depth < 0) need = __ballot_sync(0xffffffffu, !alive[r]);  // nothing stays alive: keep draining ids
+                if (a.max_depth < 0) need = __ballot_sync(0xffffffffu, !(alive_mask & bit));  // nothing stays alive: keep draining ids
             }
-            any_alive |= alive[r];
         }
-        if (!__any_sync(0xffffffffu, any_alive)) {
-            if (no_more && !u0.valid && !u1.valid) break;
+        if (!__any_sync(0xffffffffu, alive_mask != 0)) {
+            if (__all_sync(0xffffffffu, no_more && !u0.valid && !u1.valid)) break;
             continue;  // units fully claimed and nothing in flight: they retire at the top of the loop
         }
 
-        // ---------------- cast: FP32 cull scan (uniform across the warp) ...
-        double A[R];
+        // ---------------- cast: cull constants of every slot, then the FP32 scan (uniform across the warp)
+        __threadfence_block();  // accumulator zeroing (retire) is ordered before this round's atomics.  (Deliberately
+                                // not a second __syncwarp(): see tests/test_build_sass.py -- ptxas keeps the scan on
+                                // the uniform datapath only for this barrier arrangement.)
         CullRay f[R];
         int cnt[R];
         bool ovf[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            A[r] = ddot(dx[r], dy[r], dz[r], dx[r], dy[r], dz[r]);  // programs/sphere.cc:9
-            f[r] = make_cull_ray(alive[r] && a.scan_mode == 0, ox[r], oy[r], oz[r], dx[r], dy[r], dz[r], A[r]);
+            const bool live = (alive_mask >> r) & 1u;
+            const double ox = st[(0 * R + r) * kThreads], oy = st[(1 * R + r) * kThreads], oz = st[(2 * R + r) * kThreads];
+            const double dx = st[(3 * R + r) * kThreads], dy = st[(4 * R + r) * kThreads], dz = st[(5 * R + r) * kThreads];
+            const double A = dx * dx + dy * dy + dz * dz;
+            // a direction of length 0 / inf / NaN is left to the sequential FP64 scan
+            const bool sane = A > 0.0 && A < kInf;
+            f[r] = make_cull_ray(live && sane && a.scan_mode == 0, ox, oy, oz, dx, dy, dz, A);
             cnt[r] = 0;
-            ovf[r] = alive[r] && a.scan_mode != 0;
+            ovf[r] = live && (a.scan_mode != 0 || !sane);
         }
-        if (a.scan_mode == 0) cull_scan<R>(s_filt, a.sc.npad, f, cand, kThreads, cnt, ovf);
-
-        // ---------------- ... FP64 exact tests of the survivors, then shading
+        if (a.scan_mode == 0) cull_scan<R, RenderTraits<R>::kU, kConst>(s_filt, a.sc.npad, f, cand, kThreads, cnt, ovf);
+        cntpack = 0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (!alive[r]) continue;
-            ++n_casts;
-            if (ovf[r] && a.scan_mode == 0) ++n_ovf;
-            const Best best = resolve_hits(a.sc, ovf[r], cnt[r], cand + r * kThreads, R * kThreads, ox[r], oy[r], oz[r],
-                                           dx[r], dy[r], dz[r], A[r], a.tmin, kInf, n_exact);
-            if (best.k < 0) {
-                // miss: sky (programs/main.cc:46-48) * 0.5^bounces -> fixed-point accumulate
-                double cr, cg, cb;
-                sky_color(dx[r], dy[r], dz[r], A[r], bounces[r], cr, cg, cb);
-                const double fs = (double)(1ull << kFixShift);
-                unsigned long long* ap = acc + ((lpix[r] >> 6) * kTilePix + (lpix[r] & 63)) * 3;
-                atomicAdd(ap + 0, __double2ull_rz(cr * fs));
-                atomicAdd(ap + 1, __double2ull_rz(cg * fs));
-                atomicAdd(ap + 2, __double2ull_rz(cb * fs));
-                alive[r] = false;
-                continue;
-            }
-            if (bounces[r] == 0) ++n_primary;
-            if (a.early_out && best.t == 0.0 && best.C == 0.0) {
-                // origin stays on this sphere with C == 0: every later cast hits at t == 0 -> black
-                ++n_early; ++n_black;
-                alive[r] = false;
-                continue;
-            }
-            const Record rec = make_record(a.sc.exact, best, ox[r], oy[r], oz[r], dx[r], dy[r], dz[r]);
-            double rx, ry, rz;
-            random_in_hemisphere(pixid[r], smp[r], blk[r], a.key0, a.key1, rec.nx, rec.ny, rec.nz, rx, ry, rz);
-            // programs/main.cc:42-43: target = (p + normal) + rv; next ray = (p, target - p)
-            const double tgx = dadd(dadd(rec.px, rec.nx), rx);
-            const double tgy = dadd(dadd(rec.py, rec.ny), ry);
-            const double tgz = dadd(dadd(rec.pz, rec.nz), rz);
-            ox[r] = rec.px; oy[r] = rec.py; oz[r] = rec.pz;
-            dx[r] = dsub(tgx, rec.px); dy[r] = dsub(tgy, rec.py); dz[r] = dsub(tgz, rec.pz);
-            ++bounces[r];
-            if (--depth[r] < 0) {  // programs/main.cc:36-37
-                ++n_black;
-                alive[r] = false;
-            }
-        }
+        for (int r = 0; r < R; ++r) cntpack |= ((uint32_t)cnt[r] | (ovf[r] ? 0x80u : 0u)) << (8 * r);
     }
 
     // ---------------- flush counters: warp-shuffle reduce, one atomic per warp and counter
@@ -316,9 +367,10 @@ __device__ __forceinline__ Best cast_one(const SceneDev& sc, const float4* s_fil
                                          double A, double tmin, double tmax, uint32_t& n_exact, uint32_t& n_ovf) {
     CullRay f[1];
     int cnt[1] = {0};
-    bool ovf[1] = {alive && scan_mode != 0};
-    f[0] = make_cull_ray(alive && scan_mode == 0, ox, oy, oz, dx, dy, dz, A);
-    if (scan_mode == 0) cull_scan<1>(s_filt, sc.npad, f, cand, kThreads, cnt, ovf);
+    const bool sane = A > 0.0 && A < __longlong_as_double(0x7ff0000000000000ll);
+    bool ovf[1] = {alive && (scan_mode != 0 || !sane)};
+    f[0] = make_cull_ray(alive && sane && scan_mode == 0, ox, oy, oz, dx, dy, dz, A);
+    if (scan_mode == 0) cull_scan<1, 4, false>(s_filt, sc.npad, f, cand, kThreads, cnt, ovf);
     Best best;
     best.t = tmax; best.C = 1.0; best.k = -1;
     if (alive) {
@@ -333,7 +385,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads) hit_kernel(const __grid_constant__ RayBatchArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t s_mbar;
-    const SmemLayout L = smem_layout(a.sc.npad, 1);
+    const BatchSmem L = batch_smem(a.sc.npad);
     const float4* s_filt = reinterpret_cast<const float4*>(smem);
     uint16_t* cand = reinterpret_cast<uint16_t*>(smem + L.cand_off) + threadIdx.x;
     stage_bulk(smem, a.sc.filt, L.filt_bytes, &s_mbar);
@@ -384,7 +436,7 @@ __global__ void __launch_bounds__(kThreads) hit_kernel(const __grid_constant__ R
 __global__ void __launch_bounds__(kThreads) ray_color_kernel(const __grid_constant__ RayBatchArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t s_mbar;
-    const SmemLayout L = smem_layout(a.sc.npad, 1);
+    const BatchSmem L = batch_smem(a.sc.npad);
     const float4* s_filt = reinterpret_cast<const float4*>(smem);
     uint16_t* cand = reinterpret_cast<uint16_t*>(smem + L.cand_off) + threadIdx.x;
     stage_bulk(smem, a.sc.filt, L.filt_bytes, &s_mbar);

@@ -211,7 +211,8 @@ def test_render_modes_agree_bitwise(rt, book):
     cam = scenes.book_camera(W, H)
     base, bsum, _ = _render_both(rt, c, r, cam, W, H, spp, 50, 1)
     for kw in (dict(scan_mode=1), dict(early_out=False), dict(paths_per_lane=1), dict(scan_mode=1, early_out=False),
-               dict(chunks=1), dict(chunks=3), dict(chunks=8), dict(chunks=5, paths_per_lane=1)):
+               dict(chunks=1), dict(chunks=3), dict(chunks=8), dict(chunks=5, paths_per_lane=1),
+               dict(cull_smem=True), dict(cull_smem=True, paths_per_lane=1, chunks=2)):
         img, s, _ = _render_both(rt, c, r, cam, W, H, spp, 50, 1, **kw)
         assert np.array_equal(img, base), kw
         assert np.array_equal(bits(s), bits(bsum)), kw

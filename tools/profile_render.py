@@ -6,10 +6,12 @@ from petershirleyraytracer_b200 import scenes
 spp = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 eo = bool(int(sys.argv[2])) if len(sys.argv) > 2 else False
 W, H = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (1200, 800)
+ppl = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+smem = bool(int(sys.argv[6])) if len(sys.argv) > 6 else False
 c, r = scenes.book_scene(11)
 cam = scenes.book_camera(W, H)
 with rt.Scene(c, r) as sc:
-    p = rt.make_params(W, H, spp, 50, seed=1, early_out=eo)
+    p = rt.make_params(W, H, spp, 50, seed=1, early_out=eo, paths_per_lane=ppl, cull_smem=smem)
     for _ in range(2):
         _, _, st = rt.render(sc, cam, p)
 print(st)

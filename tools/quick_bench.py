@@ -24,10 +24,11 @@ if __name__ == "__main__":
     spp = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     c, r = scenes.book_scene(11)
     cam = scenes.book_camera(1200, 800)
-    for ppl in (1, 2):
-        for eo in (False, True):
-            o = run("c3", c, r, cam, 1200, 800, spp, early_out=eo, paths_per_lane=ppl)
-            print("   frac_of_peak(11 slots/test) =", round(o["gtests_s"] * 1e9 * 11 / peak, 4))
+    for smem in (False, True):
+        for ppl in (1, 2, 4):
+            for eo in (False,):
+                o = run("c3", c, r, cam, 1200, 800, spp, early_out=eo, paths_per_lane=ppl, cull_smem=smem)
+                print("   frac_of_peak(11 slots/test) =", round(o["gtests_s"] * 1e9 * 11 / peak, 4))
     dc, dr = scenes.default_scene()
     run("c1", dc, dr, rt.Camera.default(), 400, 225, 100, early_out=False)
     run("c1", dc, dr, rt.Camera.default(), 400, 225, 100, early_out=True)
