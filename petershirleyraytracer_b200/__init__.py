@@ -14,7 +14,7 @@ from dataclasses import dataclass
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "librt_b200.so")
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(PKG_DIR, "librt_b200.so")  # env override: tuning builds only
 
 SCAN_FILTERED, SCAN_EXACT, SCAN_BVH, SCAN_AUTO = 0, 1, 2, 3
 TILE_W, TILE_H = 8, 8

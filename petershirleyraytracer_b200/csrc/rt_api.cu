@@ -51,6 +51,7 @@ struct rt_scene {
     int device = 0;
     int n = 0, npad = 0;
     int sm_count = 0;
+    bool cull_ok = true;   // every sphere finite and of moderate magnitude: the FP32 cull is usable
     float4* d_filt = nullptr;
     double4* d_exact = nullptr;
     unsigned int* d_tile_counter = nullptr;   // work-queue head of the persistent warps
@@ -98,7 +99,9 @@ void tile_layout(const rt_params* p, rt_tile_layout* L) {
 
 // AUTO -> FILTERED while the cull array fits in shared memory (the BVH path takes over above that).
 int resolve_scan_mode(const rt_scene* sc, int mode, int* out) {
-    if (mode == RT_SCAN_AUTO) mode = RT_SCAN_FILTERED;
+    if (mode == RT_SCAN_AUTO) mode = (sc->cull_ok && sc->npad <= rt::kMaxLinear) ? RT_SCAN_FILTERED : RT_SCAN_EXACT;
+    if (mode == RT_SCAN_FILTERED && !sc->cull_ok)
+        return fail(RT_ERR_UNSUPPORTED, "scene has non-finite or huge (>1e15) coordinates: use RT_SCAN_EXACT");
     if (mode == RT_SCAN_BVH) return fail(RT_ERR_UNSUPPORTED, "BVH traversal is not built yet");
     if (mode == RT_SCAN_FILTERED && sc->npad > rt::kMaxLinear)
         return fail(RT_ERR_UNSUPPORTED, "linear cull scan holds at most 4064 spheres (64 KB constant bank); use RT_SCAN_EXACT or the BVH");
@@ -273,6 +276,7 @@ int rt_upload_scene(const double* centres_xyz, const double* radii, int32_t n, i
             const double Ek = rt::kCullEps * (rt::kCullKc * a2 + rt::kCullKr * r2);
             f.x = (float)cx; f.y = (float)cy; f.z = (float)cz;
             f.w = round_down_f32(a2 - r2 - Ek);
+            if (!(a2 < rt::kCullMaxMag2) || !(r2 < rt::kCullMaxMag2)) sc->cull_ok = false;  // also catches NaN / inf
             exact[k] = make_double4(cx, cy, cz, r);
         } else {
             f.x = f.y = f.z = 0.f;

@@ -32,6 +32,8 @@ enum StatSlot { ST_SAMPLES = 0, ST_CASTS, ST_SPHERE_TESTS, ST_NODE_TESTS, ST_EXA
 // 2^-24 * (40 |c|^2 + 8 r^2) into the per-sphere constant and 2^-24 * 40 |o|^2 into the per-ray constant.
 constexpr double kCullEps = 5.9604644775390625e-08;  // 2^-24
 constexpr double kCullKc = 40.0, kCullKr = 8.0, kCullKo = 40.0;
+// the FP32 cull is used only while |c|^2, r^2 and |o|^2 stay below this (no overflow / NaN in FP32)
+constexpr double kCullMaxMag2 = 1e30;
 
 // ---------------------------------------------------------------- FP64, reference evaluation order
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
@@ -43,8 +45,11 @@ __device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
 // self-hits whose numerator is exactly +-0; IEEE gives +-0 / A = +-0 for finite A > 0,
 // so that case is answered directly instead of through the division's special-operand subroutine.
 __device__ __forceinline__ double ddiv_t(double num, double A) {
-    if (num == 0.0 && A > 0.0 && A < __longlong_as_double(0x7ff0000000000000ll)) return num;
-    return __ddiv_rn(num, A);
+    const bool zero_num = num == 0.0 && A > 0.0 && A < __longlong_as_double(0x7ff0000000000000ll);
+    // the division is evaluated for every lane (the compiler if-converts it), so a zero numerator is
+    // replaced by 1.0 to keep those lanes on the fast path; their quotient is then discarded
+    const double q = __ddiv_rn(zero_num ? 1.0 : num, A);
+    return zero_num ? num : q;
 }
 // programs/vec3.h:156-159: (u0*v0 + u1*v1) + u2*v2
 __device__ __forceinline__ double ddot(double ax, double ay, double az, double bx, double by, double bz) {
@@ -140,7 +145,7 @@ struct CullRay {  // per-cast constants, 8 registers
     float dx, dy, dz;  // unit direction
     float ndo;         // -(d̂ . o)
     float mx, my, mz;  // -2 o
-    float o2;          // |o|^2 - E_o, rounded down
+    float o2;          // |o|^2 - E_o, rounded down: the pass threshold
 };
 
 // Builds the cull constants of one ray in FP64 and rounds once.  A dead slot gets constants for which no
@@ -163,25 +168,28 @@ __device__ __forceinline__ CullRay make_cull_ray(bool alive, double ox, double o
     return f;
 }
 
-// D = (d̂.(c-o))^2 - (|c-o|^2 - r^2) + E, expanded so that only 8 FP32-pipe instructions remain:
-// 3 FFMA (b) + 1 FADD + 3 FFMA (q) + 1 FFMA (D).  The sphere passes unless D < 0 (NaN passes).
+// The line through (o, d̂) can touch sphere (c, r) only if  (d̂.(c-o))^2 - |c-o|^2 + r^2 >= 0.  Expanded around
+// the world origin this is  b^2 - P >= |o|^2  with b = d̂.c - d̂.o and P = (|c|^2 - r^2) - 2 c.o, i.e. 7
+// FP32-pipe instructions per (ray, sphere): 3 FFMA (b) + 3 FFMA (P, seeded with the per-sphere constant) +
+// 1 FFMA (b*b - P); the per-sphere and per-ray constants carry the error bound, so "pass" is conservative.
 __device__ __forceinline__ float cull_D(const CullRay& f, const float4 s) {
     float b = fmaf(f.dz, s.z, f.ndo);
     b = fmaf(f.dy, s.y, b);
     b = fmaf(f.dx, s.x, b);
-    float q = s.w + f.o2;
-    q = fmaf(f.mx, s.x, q);
-    q = fmaf(f.my, s.y, q);
-    q = fmaf(f.mz, s.z, q);
-    return fmaf(b, b, -q);
+    float P = fmaf(f.mx, s.x, s.w);
+    P = fmaf(f.my, s.y, P);
+    P = fmaf(f.mz, s.z, P);
+    return fmaf(b, b, -P);  // passes unless this is < f.o2
 }
 
-// Scans the npad cull entries (kConst: constant bank, else shared memory) for R rays at once, U entries per
-// step, software-pipelined: the loads of step i+1 are issued before the arithmetic of step i (the arrays
-// carry one extra never-pass group so the last prefetch stays in bounds).  Survivors (list order) go to the
-// per-slot candidate lists cand[(e*R + r)*stride].  All lanes execute the same instruction stream; the
-// only divergent code is the (rare) append.
-template <int R, int U, bool kConst>
+// Scans the npad cull entries (kConst: constant bank, else shared memory) for R rays at once, 8 entries per
+// step in two halves, software-pipelined: each half's loads are issued one half ahead of its arithmetic
+// (the arrays carry one extra never-pass group so the last prefetch stays in bounds).  Per (ray, step) one
+// running maximum decides whether any of the 8 entries can pass; survivors (list order) go to the per-slot
+// candidate lists cand[(e*R + r)*stride].  All lanes execute the same instruction stream; the only
+// divergent code is the (rare) append.  Inputs are finite by construction (scene validated at upload, ray
+// checked by the caller), so no value here is NaN.
+template <int R, bool kConst>
 __device__ __forceinline__ void cull_scan(const float4* __restrict__ s_filt, int npad, const CullRay (&f)[R],
                                           uint16_t* cand, int stride, int (&cnt)[R], bool (&ovf)[R]) {
     // kv mirrors k in a VECTOR register (opaque to the compiler).  If the stored index were derived from
@@ -189,27 +197,30 @@ __device__ __forceinline__ void cull_scan(const float4* __restrict__ s_filt, int
     // vector registers (LDC instead of LDCU): three-register FFMAs at 63% rate instead of FFMA R,UR,R.
     int kv;
     asm volatile("mov.u32 %0, 0;" : "=r"(kv));
-    float4 s[U];
+    float4 sa[4], sb[4];
 #pragma unroll
-    for (int u = 0; u < U; ++u) s[u] = kConst ? c_filt[u] : s_filt[u];
-#pragma unroll 2
-    for (int k = 0; k < npad; k += U, kv += U) {
-        float4 nx[U];
+    for (int u = 0; u < 4; ++u) sa[u] = kConst ? c_filt[u] : s_filt[u];
+#pragma unroll 1
+    for (int k = 0; k < npad; k += 8, kv += 8) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) nx[u] = kConst ? c_filt[k + U + u] : s_filt[k + U + u];
+        for (int u = 0; u < 4; ++u) sb[u] = kConst ? c_filt[k + 4 + u] : s_filt[k + 4 + u];
+        float D[R][8];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) D[r][u] = cull_D(f[r], sa[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sa[u] = kConst ? c_filt[k + 8 + u] : s_filt[k + 8 + u];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            float D[U];
-            uint32_t all_neg = 0x80000000u;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                D[u] = cull_D(f[r], s[u]);
-                all_neg &= __float_as_uint(D[u]);
-            }
-            if ((int)all_neg >= 0) {  // at least one sign bit clear: some entry passes (or is NaN)
+            for (int u = 0; u < 4; ++u) D[r][4 + u] = cull_D(f[r], sb[u]);
+            const float m = fmaxf(fmaxf(fmaxf(D[r][0], D[r][1]), fmaxf(D[r][2], D[r][3])),
+                                  fmaxf(fmaxf(D[r][4], D[r][5]), fmaxf(D[r][6], D[r][7])));
+            if (!(m < f[r].o2)) {  // some entry of this step may be hit
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (!(D[u] < 0.f)) {
+                for (int u = 0; u < 8; ++u) {
+                    if (!(D[r][u] < f[r].o2)) {
                         if (cnt[r] < kCandCap) {
                             cand[(cnt[r] * R + r) * stride] = (uint16_t)(kv + u);
                             ++cnt[r];
@@ -220,8 +231,6 @@ __device__ __forceinline__ void cull_scan(const float4* __restrict__ s_filt, int
                 }
             }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) s[u] = nx[u];
     }
 }
 

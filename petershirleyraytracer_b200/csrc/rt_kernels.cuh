@@ -133,8 +133,16 @@ __device__ __forceinline__ void flush_unit(const RenderArgs& a, const Unit& u, u
 
 template <int R>
 struct RenderTraits {
-    static constexpr int kMinBlocks = R >= 4 ? 3 : (R == 2 ? 4 : 6);  // CTAs of 128 threads per SM (smem / register budget)
-    static constexpr int kU = 4;  // cull entries per scan step (x2 in flight: 32 uniform registers of 63)
+#ifndef RT_MINB1
+#define RT_MINB1 5
+#endif
+#ifndef RT_MINB2
+#define RT_MINB2 5
+#endif
+#ifndef RT_MINB4
+#define RT_MINB4 2
+#endif
+    static constexpr int kMinBlocks = R >= 4 ? RT_MINB4 : (R == 2 ? RT_MINB2 : RT_MINB1);  // CTAs of 128 threads per SM (register budget)
 };
 
 template <int R, bool kConst>
@@ -312,13 +320,13 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R>::kMinBlocks) render_
             const double ox = st[(0 * R + r) * kThreads], oy = st[(1 * R + r) * kThreads], oz = st[(2 * R + r) * kThreads];
             const double dx = st[(3 * R + r) * kThreads], dy = st[(4 * R + r) * kThreads], dz = st[(5 * R + r) * kThreads];
             const double A = dx * dx + dy * dy + dz * dz;
-            // a direction of length 0 / inf / NaN is left to the sequential FP64 scan
-            const bool sane = A > 0.0 && A < kInf;
+            // a direction of length 0 / inf / NaN or a far-away origin is left to the sequential FP64 scan
+            const bool sane = A > 0.0 && A < kInf && (ox * ox + oy * oy + oz * oz) < kCullMaxMag2;
             f[r] = make_cull_ray(live && sane && a.scan_mode == 0, ox, oy, oz, dx, dy, dz, A);
             cnt[r] = 0;
             ovf[r] = live && (a.scan_mode != 0 || !sane);
         }
-        if (a.scan_mode == 0) cull_scan<R, RenderTraits<R>::kU, kConst>(s_filt, a.sc.npad, f, cand, kThreads, cnt, ovf);
+        if (a.scan_mode == 0) cull_scan<R, kConst>(s_filt, a.sc.npad, f, cand, kThreads, cnt, ovf);
         cntpack = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) cntpack |= ((uint32_t)cnt[r] | (ovf[r] ? 0x80u : 0u)) << (8 * r);
@@ -367,10 +375,10 @@ __device__ __forceinline__ Best cast_one(const SceneDev& sc, const float4* s_fil
                                          double A, double tmin, double tmax, uint32_t& n_exact, uint32_t& n_ovf) {
     CullRay f[1];
     int cnt[1] = {0};
-    const bool sane = A > 0.0 && A < __longlong_as_double(0x7ff0000000000000ll);
+    const bool sane = A > 0.0 && A < __longlong_as_double(0x7ff0000000000000ll) && (ox * ox + oy * oy + oz * oz) < kCullMaxMag2;
     bool ovf[1] = {alive && (scan_mode != 0 || !sane)};
     f[0] = make_cull_ray(alive && sane && scan_mode == 0, ox, oy, oz, dx, dy, dz, A);
-    if (scan_mode == 0) cull_scan<1, 4, false>(s_filt, sc.npad, f, cand, kThreads, cnt, ovf);
+    if (scan_mode == 0) cull_scan<1, false>(s_filt, sc.npad, f, cand, kThreads, cnt, ovf);
     Best best;
     best.t = tmax; best.C = 1.0; best.k = -1;
     if (alive) {
