@@ -1,0 +1,3 @@
+// Forwarding header: the reference's "random.h" is provided by include/rt_host.hpp (add -Iinclude -Iinclude/compat).
+#pragma once
+#include "../rt_host.hpp"

@@ -55,11 +55,13 @@ def build_host_main(force: bool = False) -> str | None:
     src = os.path.join(PKG_DIR, "host", "main.cc")
     if not os.path.exists(src):
         return None
-    deps = [src] + [os.path.join(REPO, "include", f) for f in os.listdir(os.path.join(REPO, "include"))]
+    deps = [src] + [os.path.join(REPO, "include", f) for f in os.listdir(os.path.join(REPO, "include"))
+                    if os.path.isfile(os.path.join(REPO, "include", f))]
     if not force and _newer(HOST_MAIN, deps + [LIB_PATH]):
         return HOST_MAIN
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [cxx, "-O2", "-std=c++17", "-I", os.path.join(REPO, "include"), src, "-o", HOST_MAIN,
+    cmd = [cxx, "-O2", "-std=c++17", "-I", os.path.join(REPO, "include"), "-I", os.path.join(REPO, "include", "compat"),
+           src, "-o", HOST_MAIN,
            "-L", PKG_DIR, "-lrt_b200", "-Wl,-rpath,$ORIGIN"]
     subprocess.run(cmd, check=True, cwd=PKG_DIR)
     return HOST_MAIN

@@ -46,9 +46,13 @@ __device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
 // so that case is answered directly instead of through the division's special-operand subroutine.
 __device__ __forceinline__ double ddiv_t(double num, double A) {
     const bool zero_num = num == 0.0 && A > 0.0 && A < __longlong_as_double(0x7ff0000000000000ll);
-    // the division is evaluated for every lane (the compiler if-converts it), so a zero numerator is
-    // replaced by 1.0 to keep those lanes on the fast path; their quotient is then discarded
-    const double q = __ddiv_rn(zero_num ? 1.0 : num, A);
+    // The division is evaluated for every lane (the compiler if-converts it), so a zero numerator is
+    // replaced by 1.0 to keep those lanes off the special-operand subroutine; their quotient is discarded.
+    // The empty asm hides the substitution from the optimiser, which otherwise proves the quotient unused
+    // for those lanes and feeds the zero straight back into the division.
+    double safe = zero_num ? 1.0 : num;
+    asm volatile("" : "+d"(safe));
+    const double q = __ddiv_rn(safe, A);
     return zero_num ? num : q;
 }
 // programs/vec3.h:156-159: (u0*v0 + u1*v1) + u2*v2

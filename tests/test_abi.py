@@ -71,6 +71,7 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cc", ".h", ".hpp")):
                 text = open(os.path.join(root, f), errors="replace").read()
                 assert "liboracle" not in text and "libref" not in text and "oracle_lib" not in text, f
-    for f in os.listdir(os.path.join(REPO, "include")):
-        text = open(os.path.join(REPO, "include", f)).read()
-        assert "liboracle" not in text and "rt_oracle" not in text, f
+    for root, _, files in os.walk(os.path.join(REPO, "include")):
+        for f in files:
+            text = open(os.path.join(root, f)).read()
+            assert "liboracle" not in text and "rt_oracle" not in text, f

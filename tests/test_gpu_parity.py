@@ -287,3 +287,37 @@ def test_sharded_tiles_reassemble_to_the_same_frame(rt, book):
             rt.deinterleave(p0, gathered.data_ptr(), frame.data_ptr(), 0)
             torch.cuda.synchronize()
             assert np.array_equal(frame.cpu().numpy().reshape(H, W, 4), full), world
+
+
+# ------------------------------------------------------------------ C++ host API (include/rt_host.hpp)
+def test_host_main_prints_the_oracle_frame_as_p3(rt, default_scene):
+    """petershirleyraytracer_b200/rt_main = the reference's main() shape on the GPU path; its P3 text must be
+    the oracle's frame for the same Philox key."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(rt.LIB_PATH), "rt_main")
+    if not os.path.exists(exe):
+        pytest.skip("rt_main not built")
+    W, spp, depth, seed = 120, 8, 50, 5
+    out = subprocess.run([exe, str(W), str(spp), str(depth), str(seed)], capture_output=True, check=True).stdout.decode()
+    lines = out.split("\n")
+    H = int(W / (16.0 / 9.0))
+    assert lines[0] == "P3" and lines[1] == f"{W} {H}" and lines[2] == "255"
+    px = np.array([[int(v) for v in ln.split()] for ln in lines[3:3 + W * H]], dtype=np.uint8).reshape(H, W, 3)
+    c, r = default_scene
+    orgb, _, _ = ol.render("orc", c, r, rt.Camera.default().as12(), W, H, spp, depth, seed=seed, rng_mode=ol.RNG_PHILOX)
+    assert np.array_equal(px, orgb)
+
+
+def test_dist_module_single_rank(rt, book):
+    import torch
+    from petershirleyraytracer_b200 import dist as rdist, scenes
+    c, r = book
+    W, H = 72, 48
+    cam = scenes.book_camera(W, H)
+    p = rt.make_params(W, H, 4, 50, seed=2)
+    with rt.Scene(c, r) as sc:
+        full, _, _ = rt.render(sc, cam, p)
+        frame = rdist.render_sharded(sc, cam, p, 0, 1)
+        torch.cuda.synchronize()
+        assert np.array_equal(frame.cpu().numpy(), full)
