@@ -104,7 +104,7 @@ int resolve_scan_mode(const rt_scene* sc, int mode, int* out) {
         return fail(RT_ERR_UNSUPPORTED, "scene has non-finite or huge (>1e15) coordinates: use RT_SCAN_EXACT");
     if (mode == RT_SCAN_BVH) return fail(RT_ERR_UNSUPPORTED, "BVH traversal is not built yet");
     if (mode == RT_SCAN_FILTERED && sc->npad > rt::kMaxLinear)
-        return fail(RT_ERR_UNSUPPORTED, "linear cull scan holds at most 4064 spheres (64 KB constant bank); use RT_SCAN_EXACT or the BVH");
+        return fail(RT_ERR_UNSUPPORTED, "linear cull scan holds at most 4080 spheres (64 KB constant bank); use RT_SCAN_EXACT or the BVH");
     *out = mode;
     return RT_OK;
 }
@@ -260,7 +260,7 @@ int rt_upload_scene(const double* centres_xyz, const double* radii, int32_t n, i
     rt_scene* sc = new (std::nothrow) rt_scene();
     if (!sc) return fail(RT_ERR_NOMEM, "host allocation failed");
     sc->device = device; sc->n = n;
-    sc->npad = (n + rt::kScanPad - 1) / rt::kScanPad * rt::kScanPad;  // the arrays carry kScanPad more never-pass entries
+    sc->npad = (n + rt::kScanStep - 1) / rt::kScanStep * rt::kScanStep;  // the arrays carry kScanPad more never-pass entries
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete sc; return fail(RT_ERR_CUDA, "cudaGetDeviceProperties failed"); }
     sc->sm_count = prop.multiProcessorCount;

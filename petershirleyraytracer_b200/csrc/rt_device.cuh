@@ -19,8 +19,9 @@ constexpr int kTileW = 8, kTileH = 8, kTilePix = kTileW * kTileH;  // one warp r
 constexpr int kThreads = 128;                                       // 4 warps per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kCandCap = 12;        // survivors per cast kept in smem; more -> full FP64 scan for that cast
-constexpr int kScanPad = 8;         // cull arrays are padded to a multiple of this, plus one extra group (prefetch)
-constexpr int kMaxLinear = 4064;    // cull entries that fit the 64 KB constant bank (with the prefetch pad)
+constexpr int kScanStep = 12;       // cull entries per scan step; arrays are padded to a multiple of this ...
+constexpr int kScanPad = 8;         // ... plus this many never-pass entries (prefetch runs two groups ahead)
+constexpr int kMaxLinear = 4080;    // cull entries that fit the 64 KB constant bank (with the prefetch pad)
 constexpr int kFixShift = 44;       // radiance accumulates as 20.44 fixed point (order-independent sums)
 constexpr int kNumStats = 10;
 
@@ -186,13 +187,14 @@ __device__ __forceinline__ float cull_D(const CullRay& f, const float4 s) {
     return fmaf(b, b, -P);  // passes unless this is < f.o2
 }
 
-// Scans the npad cull entries (kConst: constant bank, else shared memory) for R rays at once, 8 entries per
-// step in two halves, software-pipelined: each half's loads are issued one half ahead of its arithmetic
-// (the arrays carry one extra never-pass group so the last prefetch stays in bounds).  Per (ray, step) one
-// running maximum decides whether any of the 8 entries can pass; survivors (list order) go to the per-slot
-// candidate lists cand[(e*R + r)*stride].  All lanes execute the same instruction stream; the only
-// divergent code is the (rare) append.  Inputs are finite by construction (scene validated at upload, ray
-// checked by the caller), so no value here is NaN.
+// Scans the npad cull entries (kConst: constant bank, else shared memory) for R rays at once, 12 entries per
+// step in three groups of 4, software-pipelined two groups deep: while group g is evaluated, the loads of
+// groups g+1 and g+2 are in flight (48 of the 63 uniform registers; the arrays carry 8 extra never-pass
+// entries so the last prefetches stay in bounds).  Per (ray, step) one running maximum decides whether any
+// of the 12 entries can pass; survivors (list order) go to the per-slot candidate lists
+// cand[(e*R + r)*stride].  All lanes execute the same instruction stream; the only divergent code is the
+// (rare) append.  Inputs are finite by construction (scene validated at upload, ray checked by the caller),
+// so no value here is NaN.
 template <int R, bool kConst>
 __device__ __forceinline__ void cull_scan(const float4* __restrict__ s_filt, int npad, const CullRay (&f)[R],
                                           uint16_t* cand, int stride, int (&cnt)[R], bool (&ovf)[R]) {
@@ -201,29 +203,46 @@ __device__ __forceinline__ void cull_scan(const float4* __restrict__ s_filt, int
     // vector registers (LDC instead of LDCU): three-register FFMAs at 63% rate instead of FFMA R,UR,R.
     int kv;
     asm volatile("mov.u32 %0, 0;" : "=r"(kv));
-    float4 sa[4], sb[4];
+    float4 g0[4], g1[4], g2[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) sa[u] = kConst ? c_filt[u] : s_filt[u];
+    for (int u = 0; u < 4; ++u) {
+        g0[u] = kConst ? c_filt[u] : s_filt[u];
+        g1[u] = kConst ? c_filt[4 + u] : s_filt[4 + u];
+    }
 #pragma unroll 1
-    for (int k = 0; k < npad; k += 8, kv += 8) {
+    for (int k = 0; k < npad; k += kScanStep, kv += kScanStep) {
+        float D[R][kScanStep];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) sb[u] = kConst ? c_filt[k + 4 + u] : s_filt[k + 4 + u];
-        float D[R][8];
+        for (int u = 0; u < 4; ++u) g2[u] = kConst ? c_filt[k + 8 + u] : s_filt[k + 8 + u];
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int u = 0; u < 4; ++u) D[r][u] = cull_D(f[r], sa[u]);
+            for (int u = 0; u < 4; ++u) D[r][u] = cull_D(f[r], g0[u]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) sa[u] = kConst ? c_filt[k + 8 + u] : s_filt[k + 8 + u];
+        for (int u = 0; u < 4; ++u) g0[u] = kConst ? c_filt[k + 12 + u] : s_filt[k + 12 + u];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) D[r][4 + u] = cull_D(f[r], g1[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) g1[u] = kConst ? c_filt[k + 16 + u] : s_filt[k + 16 + u];
+        bool any = false;
+        float m[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) D[r][4 + u] = cull_D(f[r], sb[u]);
-            const float m = fmaxf(fmaxf(fmaxf(D[r][0], D[r][1]), fmaxf(D[r][2], D[r][3])),
-                                  fmaxf(fmaxf(D[r][4], D[r][5]), fmaxf(D[r][6], D[r][7])));
-            if (!(m < f[r].o2)) {  // some entry of this step may be hit
+            for (int u = 0; u < 4; ++u) D[r][8 + u] = cull_D(f[r], g2[u]);
+            m[r] = fmaxf(fmaxf(fmaxf(D[r][0], D[r][1]), fmaxf(D[r][2], D[r][3])),
+                         fmaxf(fmaxf(fmaxf(D[r][4], D[r][5]), fmaxf(D[r][6], D[r][7])),
+                               fmaxf(fmaxf(D[r][8], D[r][9]), fmaxf(D[r][10], D[r][11]))));
+            any |= !(m[r] < f[r].o2);
+        }
+        if (any) {  // some entry of this step may be hit by one of this lane's rays
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+            for (int r = 0; r < R; ++r) {
+                if (m[r] < f[r].o2) continue;
+#pragma unroll
+                for (int u = 0; u < kScanStep; ++u) {
                     if (!(D[r][u] < f[r].o2)) {
                         if (cnt[r] < kCandCap) {
                             cand[(cnt[r] * R + r) * stride] = (uint16_t)(kv + u);
