@@ -1,6 +1,7 @@
 // rt_api.cu -- the C ABI of include/rt.h over the sm_100a kernels in rt_kernels.cuh.
 // Host side only flattens, uploads, launches and copies; there is no CPU implementation of the path.
 #include "../../include/rt.h"
+#include "rt_bvh.h"
 #include "rt_kernels.cuh"
 
 #include <cmath>
@@ -54,6 +55,9 @@ struct rt_scene {
     bool cull_ok = true;   // every sphere finite and of moderate magnitude: the FP32 cull is usable
     float4* d_filt = nullptr;
     double4* d_exact = nullptr;
+    float4* d_bvh_nodes = nullptr;    // flattened BVH (rt_bvh.h), built at upload
+    int32_t* d_bvh_leaf = nullptr;
+    int bvh_nodes = 0;
     unsigned int* d_tile_counter = nullptr;   // work-queue head of the persistent warps
     unsigned long long* d_stats = nullptr;
     void* d_accum = nullptr; size_t accum_cap = 0;   // fixed-point radiance per tile pixel (+ chunk counters behind it)
@@ -99,10 +103,12 @@ void tile_layout(const rt_params* p, rt_tile_layout* L) {
 
 // AUTO -> FILTERED while the cull array fits in shared memory (the BVH path takes over above that).
 int resolve_scan_mode(const rt_scene* sc, int mode, int* out) {
-    if (mode == RT_SCAN_AUTO) mode = (sc->cull_ok && sc->npad <= rt::kMaxLinear) ? RT_SCAN_FILTERED : RT_SCAN_EXACT;
+    // AUTO: the linear cull scan while it is cheaper than a traversal, the BVH for large scenes
+    if (mode == RT_SCAN_AUTO) mode = (sc->cull_ok && sc->n <= 1024) ? RT_SCAN_FILTERED : RT_SCAN_BVH;
     if (mode == RT_SCAN_FILTERED && !sc->cull_ok)
         return fail(RT_ERR_UNSUPPORTED, "scene has non-finite or huge (>1e15) coordinates: use RT_SCAN_EXACT");
-    if (mode == RT_SCAN_BVH) return fail(RT_ERR_UNSUPPORTED, "BVH traversal is not built yet");
+    if (mode == RT_SCAN_BVH && !sc->d_bvh_nodes)
+        return fail(RT_ERR_UNSUPPORTED, "no BVH for this scene (non-finite or huge coordinates): use RT_SCAN_EXACT");
     if (mode == RT_SCAN_FILTERED && sc->npad > rt::kMaxLinear)
         return fail(RT_ERR_UNSUPPORTED, "linear cull scan holds at most 4080 spheres (64 KB constant bank); use RT_SCAN_EXACT or the BVH");
     *out = mode;
@@ -112,7 +118,8 @@ int resolve_scan_mode(const rt_scene* sc, int mode, int* out) {
 rt::SceneDev scene_dev(const rt_scene* sc, int mode) {
     rt::SceneDev d;
     d.filt = sc->d_filt; d.exact = sc->d_exact; d.n = sc->n;
-    d.npad = (mode == RT_SCAN_FILTERED) ? sc->npad : 0;  // EXACT stages nothing
+    d.npad = (mode == RT_SCAN_FILTERED) ? sc->npad : 0;  // EXACT / BVH stage nothing
+    d.bvh_nodes = sc->d_bvh_nodes; d.bvh_leaf = sc->d_bvh_leaf;
     return d;
 }
 
@@ -154,6 +161,7 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     int R = p->reserved[0];
     if (R == 0) R = 2;
     if (R != 1 && R != 2 && R != 4) return fail(RT_ERR_INVALID, "reserved[0] (paths per lane) must be 0, 1, 2 or 4");
+    if (mode == RT_SCAN_BVH) R = 1;  // traversal is divergent: one path per lane, more warps
     // cull array source: constant bank (default; FFMAs then read a uniform-register operand) or the
     // TMA-staged shared-memory copy (reserved[2] == 1), kept for A/B evidence
     const bool use_const = p->reserved[2] != 1 && mode == RT_SCAN_FILTERED;
@@ -163,8 +171,9 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     }
     const rt::RenderSmem S = rt::render_smem(use_const ? 0 : a.sc.npad, R);
     void (*kern)(const rt::RenderArgs) = nullptr;
-    if (use_const) kern = R == 1 ? rt::render_kernel<1, true> : (R == 2 ? rt::render_kernel<2, true> : rt::render_kernel<4, true>);
-    else kern = R == 1 ? rt::render_kernel<1, false> : (R == 2 ? rt::render_kernel<2, false> : rt::render_kernel<4, false>);
+    if (mode == RT_SCAN_BVH) kern = rt::render_kernel<1, 2>;
+    else if (use_const) kern = R == 1 ? rt::render_kernel<1, 1> : (R == 2 ? rt::render_kernel<2, 1> : rt::render_kernel<4, 1>);
+    else kern = R == 1 ? rt::render_kernel<1, 0> : (R == 2 ? rt::render_kernel<2, 0> : rt::render_kernel<4, 0>);
     RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
     int per_sm = 0;
     RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, rt::kThreads, S.total));
@@ -220,7 +229,8 @@ int finish_render(rt_scene* sc, rt_stats* st) {
     st->kernel_ms = ms;
     st->samples = h[rt::ST_SAMPLES]; st->casts = h[rt::ST_CASTS];
     st->sphere_tests = (sc->last_mode == RT_SCAN_FILTERED) ? h[rt::ST_CASTS] * (uint64_t)sc->n : 0;
-    st->node_tests = h[rt::ST_NODE_TESTS]; st->exact_tests = h[rt::ST_EXACT_TESTS];
+    st->node_tests = 2 * h[rt::ST_NODE_TESTS];  // two child boxes per visited node
+    st->exact_tests = h[rt::ST_EXACT_TESTS];
     st->black = h[rt::ST_BLACK]; st->early_outs = h[rt::ST_EARLY_OUTS];
     st->primary_hits = h[rt::ST_PRIMARY_HITS]; st->overflows = h[rt::ST_OVERFLOWS];
     st->launches = sc->last_launches;
@@ -254,7 +264,7 @@ int rt_upload_scene(const double* centres_xyz, const double* radii, int32_t n, i
     if (!out) return fail(RT_ERR_INVALID, "out is NULL");
     *out = nullptr;
     if (n < 0 || (n > 0 && (!centres_xyz || !radii))) return fail(RT_ERR_INVALID, "bad sphere arrays");
-    if (n > 65535) return fail(RT_ERR_UNSUPPORTED, "more than 65535 spheres needs the BVH path (not built yet)");
+    if (n > (1 << 27)) return fail(RT_ERR_UNSUPPORTED, "at most 2^27 spheres");
     DeviceGuard guard(device);
     if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed (no CUDA device?)");
     rt_scene* sc = new (std::nothrow) rt_scene();
@@ -293,6 +303,17 @@ int rt_upload_scene(const double* centres_xyz, const double* radii, int32_t n, i
         if (cudaMemcpy(sc->d_filt, filt.data(), filt.size() * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess ||
             cudaMemcpy(sc->d_exact, exact.data(), exact.size() * sizeof(double4), cudaMemcpyHostToDevice) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
         if (cudaEventCreate(&sc->ev0) != cudaSuccess || cudaEventCreate(&sc->ev1) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
+        // flattened BVH (exact closest-hit semantics, rt_bvh.h); finite scenes only
+        if (sc->cull_ok) {
+            rt::BvhHost bvh;
+            rt::build_bvh(centres_xyz, radii, n, &bvh);
+            sc->bvh_nodes = (int)bvh.nodes.size();
+            const size_t nb = bvh.nodes.size() * sizeof(rt::BvhNode), lb = (bvh.leaf_idx.size() + 1) * sizeof(int32_t);
+            if (cudaMalloc(&sc->d_bvh_nodes, nb) != cudaSuccess || cudaMalloc(&sc->d_bvh_leaf, lb) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
+            if (cudaMemcpy(sc->d_bvh_nodes, bvh.nodes.data(), nb, cudaMemcpyHostToDevice) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
+            if (!bvh.leaf_idx.empty() &&
+                cudaMemcpy(sc->d_bvh_leaf, bvh.leaf_idx.data(), bvh.leaf_idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
+        }
     } while (0);
     if (rc != RT_OK) {
         const std::string msg = std::string("scene upload: ") + cudaGetErrorString(cudaGetLastError());
@@ -308,6 +329,7 @@ void rt_free_scene(rt_scene* sc) {
     DeviceGuard guard(sc->device);
     if (sc->pending) cudaEventSynchronize(sc->ev1);
     cudaFree(sc->d_filt); cudaFree(sc->d_exact); cudaFree(sc->d_tile_counter); cudaFree(sc->d_stats);
+    cudaFree(sc->d_bvh_nodes); cudaFree(sc->d_bvh_leaf);
     cudaFree(sc->d_frame); cudaFree(sc->d_sum); cudaFree(sc->d_accum);
     if (sc->ev0) cudaEventDestroy(sc->ev0);
     if (sc->ev1) cudaEventDestroy(sc->ev1);

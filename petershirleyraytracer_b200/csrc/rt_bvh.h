@@ -1,0 +1,128 @@
+// rt_bvh.h -- host-side build of the flattened BVH used for scenes too large for the linear cull scan
+// (BASELINE config 4: ~100k spheres).  The reference has no acceleration structure: hittable_list::hit
+// (programs/hittable_list.cc:3-20) tests every object.  Its result -- the smallest accepted t, ties going to
+// the LATER list index -- does not depend on the order in which objects are visited, so a BVH may replace
+// the scan as long as (a) no box that the ray's hit sphere lies in is ever skipped and (b) a subtree is pruned
+// only when its entry distance is strictly beyond the current best.  Boxes are therefore stored in FP32
+// rounded OUTWARD and padded; the device test adds the per-ray padding (rt_device.cuh: bvh_cast).
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+namespace rt {
+
+// Two children per node, both boxes inline: one 64-byte fetch decides both subtrees.
+struct BvhNode {
+    float lo0[3], hi0[3];
+    float lo1[3], hi1[3];
+    int32_t child0, child1;  // >= 0: node index; < 0: leaf = 0x80000000 | first << 3 | count (count <= 4)
+    int32_t pad[2];
+};
+static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
+
+constexpr int kBvhLeafMax = 4;
+
+struct BvhHost {
+    std::vector<BvhNode> nodes;     // nodes[0] = root
+    std::vector<int32_t> leaf_idx;  // sphere list indices, leaf by leaf
+};
+
+namespace bvh_detail {
+
+struct Box { double lo[3], hi[3]; };
+
+inline float down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return f; }
+inline float up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return f; }
+
+inline void store_box(const Box& b, float* lo, float* hi) {
+    for (int a = 0; a < 3; ++a) {
+        // pad: 2^-20 of the coordinate magnitude covers FP32 rounding of the box, of the ray origin and of
+        // the subtraction in the slab test; the reference's own FP64 slop is 2^-32 of that
+        const double mag = std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a]));
+        const double pad = mag * 9.5367431640625e-07 + 1e-30;
+        lo[a] = down(b.lo[a] - pad);
+        hi[a] = up(b.hi[a] + pad);
+    }
+}
+
+inline void empty_box(float* lo, float* hi) {
+    for (int a = 0; a < 3; ++a) { lo[a] = INFINITY; hi[a] = -INFINITY; }
+}
+
+struct Builder {
+    const double* c; const double* r;
+    std::vector<int32_t> order;
+    BvhHost* out;
+
+    Box bounds(int first, int count) const {
+        Box b;
+        for (int a = 0; a < 3; ++a) { b.lo[a] = INFINITY; b.hi[a] = -INFINITY; }
+        for (int i = first; i < first + count; ++i) {
+            const int k = order[i];
+            const double rad = std::fabs(r[k]);
+            for (int a = 0; a < 3; ++a) {
+                b.lo[a] = std::min(b.lo[a], c[3 * k + a] - rad);
+                b.hi[a] = std::max(b.hi[a], c[3 * k + a] + rad);
+            }
+        }
+        return b;
+    }
+
+    // returns the child reference for spheres order[first, first+count)
+    int32_t build(int first, int count) {
+        if (count <= kBvhLeafMax) {
+            const int32_t at = (int32_t)out->leaf_idx.size();
+            // inside a leaf keep list order (not required for correctness; keeps tests readable)
+            std::sort(order.begin() + first, order.begin() + first + count);
+            for (int i = 0; i < count; ++i) out->leaf_idx.push_back(order[first + i]);
+            return (int32_t)(0x80000000u | ((uint32_t)at << 3) | (uint32_t)count);
+        }
+        // split at the object median of the centroid axis with the largest extent
+        double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int i = first; i < first + count; ++i)
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = std::min(lo[a], c[3 * order[i] + a]);
+                hi[a] = std::max(hi[a], c[3 * order[i] + a]);
+            }
+        int axis = 0;
+        for (int a = 1; a < 3; ++a) if (hi[a] - lo[a] > hi[axis] - lo[axis]) axis = a;
+        const int mid = count / 2;
+        std::nth_element(order.begin() + first, order.begin() + first + mid, order.begin() + first + count,
+                         [&](int32_t x, int32_t y) { return c[3 * x + axis] < c[3 * y + axis]; });
+        const int32_t me = (int32_t)out->nodes.size();
+        out->nodes.push_back(BvhNode{});
+        const Box b0 = bounds(first, mid), b1 = bounds(first + mid, count - mid);
+        const int32_t c0 = build(first, mid);
+        const int32_t c1 = build(first + mid, count - mid);
+        BvhNode& n = out->nodes[me];
+        store_box(b0, n.lo0, n.hi0);
+        store_box(b1, n.lo1, n.hi1);
+        n.child0 = c0; n.child1 = c1;
+        return me;
+    }
+};
+
+}  // namespace bvh_detail
+
+inline void build_bvh(const double* centres, const double* radii, int n, BvhHost* out) {
+    using namespace bvh_detail;
+    out->nodes.clear(); out->leaf_idx.clear();
+    Builder b{centres, radii, {}, out};
+    b.order.resize(n);
+    for (int i = 0; i < n; ++i) b.order[i] = i;
+    if (n <= kBvhLeafMax) {  // root must be a node: one real leaf + one empty child
+        out->nodes.push_back(BvhNode{});
+        const int32_t leaf = n > 0 ? b.build(0, n) : (int32_t)0x80000000u;
+        BvhNode& root = out->nodes[0];
+        if (n > 0) store_box(b.bounds(0, n), root.lo0, root.hi0); else empty_box(root.lo0, root.hi0);
+        empty_box(root.lo1, root.hi1);
+        root.child0 = leaf; root.child1 = (int32_t)0x80000000u;
+        return;
+    }
+    b.build(0, n);  // nodes[0] is the root because the first push_back happens at the top call
+}
+
+}  // namespace rt

@@ -83,6 +83,8 @@ struct SceneDev {
     const float4* filt;    // npad entries {cx, cy, cz, |c|^2 - r^2 - E_k} (FP32 cull), padded with never-pass entries
     const double4* exact;  // n entries {cx, cy, cz, r} (FP64, list order)
     int n, npad;
+    const float4* bvh_nodes;   // 4 float4 per node (rt_bvh.h: BvhNode), root = node 0; NULL if not built
+    const int32_t* bvh_leaf;   // sphere list indices, leaf by leaf
 };
 
 struct RenderArgs {
@@ -308,6 +310,119 @@ __device__ __forceinline__ Record make_record(const double4* __restrict__ exact,
     rec.ny = rec.front_face ? wy : -wy;
     rec.nz = rec.front_face ? wz : -wz;
     return rec;
+}
+
+// sphere::hit for sphere k with the caller's fixed [tmin, tmax] (programs/sphere.cc:3-32), merged into `best` by
+// the ORDER-INDEPENDENT form of hittable_list.cc:9-17: the list scan keeps the smallest accepted t and, on
+// equal t, the later index.  (Equivalent because the far root is never smaller than the near root, so a sphere
+// whose near root lies beyond closest_so_far is rejected either way.)  Used by the BVH traversal, which
+// meets spheres in tree order.
+__device__ __forceinline__ bool exact_test_unordered(const double4* __restrict__ exact, int k, double ox, double oy,
+                                                     double oz, double dx, double dy, double dz, double A, double tmin,
+                                                     double tmax, Best& best) {
+    const double2 c01 = __ldg(reinterpret_cast<const double2*>(exact + k));
+    const double2 c23 = __ldg(reinterpret_cast<const double2*>(exact + k) + 1);
+    const double amx = dsub(ox, c01.x), amy = dsub(oy, c01.y), amz = dsub(oz, c23.x);
+    const double HALF_B = ddot(dx, dy, dz, amx, amy, amz);
+    const double C = dsub(ddot(amx, amy, amz, amx, amy, amz), dmul(c23.y, c23.y));
+    const double disc = dsub(dmul(HALF_B, HALF_B), dmul(A, C));
+    if (disc < 0) return false;
+    const double sqrt_d = dsqrt(disc);
+    double t = ddiv_t(dsub(-HALF_B, sqrt_d), A);
+    if (t < tmin || t > tmax) {
+        t = ddiv_t(dadd(-HALF_B, sqrt_d), A);
+        if (t < tmin || t > tmax) return false;
+    }
+    if (best.k < 0 || t < best.t || (t == best.t && k > best.k)) {
+        best.t = t; best.C = C; best.k = k;
+        return true;
+    }
+    return false;
+}
+
+// Closest hit through the flattened BVH (rt_bvh.h), exact semantics: box tests are conservative FP32 slab
+// tests (boxes rounded outward and padded at build time; the ray origin is widened by its own FP32 rounding
+// here), a subtree is skipped only if it is missed or its entry distance is strictly beyond the current
+// best, and every sphere of a visited leaf runs the FP64 test above.  Requires tmin >= 0 and a finite,
+// non-zero direction (callers route other rays to the sequential scan).  Nearer child first.
+constexpr int kBvhStack = 40;
+__device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double oy, double oz, double dx, double dy,
+                                         double dz, double A, double tmin, double tmax, uint32_t& n_exact,
+                                         uint32_t& n_nodes, bool& overflow) {
+    Best best;
+    best.t = tmax; best.C = 1.0; best.k = -1;
+    const float kUp = 1.0f + 1.9073486328125e-06f, kDn = 1.0f - 1.9073486328125e-06f;  // 1 +- 2^-19
+    const float fx = (float)ox, fy = (float)oy, fz = (float)oz;
+    const float padx = fabsf(fx) * 2.384185791015625e-07f + 1e-37f, pady = fabsf(fy) * 2.384185791015625e-07f + 1e-37f,
+                padz = fabsf(fz) * 2.384185791015625e-07f + 1e-37f;  // 2^-22 |o|: covers the FP32 rounding of o
+    const float opx = __fadd_ru(fx, padx), opy = __fadd_ru(fy, pady), opz = __fadd_ru(fz, padz);
+    const float omx = __fadd_rd(fx, -padx), omy = __fadd_rd(fy, -pady), omz = __fadd_rd(fz, -padz);
+    const float ivx = (float)(1.0 / dx), ivy = (float)(1.0 / dy), ivz = (float)(1.0 / dz);
+    float best_up = __double2float_ru(tmax);
+    int stack_n[kBvhStack];
+    float stack_t[kBvhStack];
+    int sp = 0, node = 0;
+    for (;;) {
+        const float4 q0 = __ldg(sc.bvh_nodes + 4 * node), q1 = __ldg(sc.bvh_nodes + 4 * node + 1);
+        const float4 q2 = __ldg(sc.bvh_nodes + 4 * node + 2), q3 = __ldg(sc.bvh_nodes + 4 * node + 3);
+        ++n_nodes;
+        const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+        float tn0, tn1;
+        bool h0, h1;
+        {
+            const float ax = (q0.x - opx) * ivx, bx = (q0.w - omx) * ivx;
+            const float ay = (q0.y - opy) * ivy, by = (q1.x - omy) * ivy;
+            const float az = (q0.z - opz) * ivz, bz = (q1.y - omz) * ivz;
+            tn0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+            const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+            h0 = tn0 <= tf * kUp && tn0 * kDn <= best_up;
+        }
+        {
+            const float ax = (q1.z - opx) * ivx, bx = (q2.y - omx) * ivx;
+            const float ay = (q1.w - opy) * ivy, by = (q2.z - omy) * ivy;
+            const float az = (q2.x - opz) * ivz, bz = (q2.w - omz) * ivz;
+            tn1 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+            const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+            h1 = tn1 <= tf * kUp && tn1 * kDn <= best_up;
+        }
+        // leaves are resolved on the spot (the nearer one first), inner children go to the stack
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool first0 = tn0 <= tn1;
+            const bool use0 = (pass == 0) == first0;
+            const int c = use0 ? c0 : c1;
+            const bool h = use0 ? h0 : h1;
+            const float tn = use0 ? tn0 : tn1;
+            if (h && c < 0 && tn * kDn <= best_up) {
+                const int first = (int)(((unsigned)c & 0x7fffffffu) >> 3), count = c & 7;
+                for (int i = 0; i < count; ++i) {
+                    const int k = __ldg(sc.bvh_leaf + first + i);
+                    ++n_exact;
+                    if (exact_test_unordered(sc.exact, k, ox, oy, oz, dx, dy, dz, A, tmin, tmax, best))
+                        best_up = __double2float_ru(best.t);
+                }
+            }
+        }
+        const bool in0 = h0 && c0 >= 0 && tn0 * kDn <= best_up, in1 = h1 && c1 >= 0 && tn1 * kDn <= best_up;
+        if (in0 && in1) {
+            const bool near0 = tn0 <= tn1;
+            if (sp >= kBvhStack) { overflow = true; return best; }
+            stack_n[sp] = near0 ? c1 : c0; stack_t[sp] = near0 ? tn1 : tn0; ++sp;
+            node = near0 ? c0 : c1;
+        } else if (in0) {
+            node = c0;
+        } else if (in1) {
+            node = c1;
+        } else {
+            bool found = false;
+            while (sp > 0) {
+                --sp;
+                if (stack_t[sp] * kDn <= best_up) { node = stack_n[sp]; found = true; break; }
+            }
+            if (!found) break;
+        }
+    }
+    return best;
 }
 
 // hittable_list::hit for one ray given its survivors (or the full list when ovf): list order, shrinking tmax.

@@ -145,11 +145,14 @@ struct RenderTraits {
     static constexpr int kMinBlocks = R >= 4 ? RT_MINB4 : (R == 2 ? RT_MINB2 : RT_MINB1);  // CTAs of 128 threads per SM (register budget)
 };
 
-template <int R, bool kConst>
+// kSrc: where the cast looks for hits: 0 = cull array in TMA-staged shared memory, 1 = cull array in the
+// constant bank (default), 2 = flattened BVH (large scenes)
+template <int R, int kSrc>
 __global__ void __launch_bounds__(kThreads, RenderTraits<R>::kMinBlocks) render_kernel(const __grid_constant__ RenderArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t s_mbar;
-    const RenderSmem L = render_smem(kConst ? 0 : a.sc.npad, R);
+    constexpr bool kConst = kSrc == 1, kBvh = kSrc == 2;
+    const RenderSmem L = render_smem(kSrc == 0 ? a.sc.npad : 0, R);
     const float4* s_filt = reinterpret_cast<const float4*>(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // two accumulator buffers per warp: the next unit starts while the last paths of the previous one finish
@@ -160,14 +163,17 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R>::kMinBlocks) render_
 
 #pragma unroll
     for (int j = 0; j < 2 * kTilePix * 3 / 32; ++j) acc[j * 32 + lane] = 0ull;
-    if (!kConst) stage_bulk(smem, a.sc.filt, L.filt_bytes, &s_mbar);
+    if (kSrc == 0) stage_bulk(smem, a.sc.filt, L.filt_bytes, &s_mbar);
 
     const double wm1 = (double)(a.W - 1), hm1 = (double)(a.H - 1);
     const double kInf = __longlong_as_double(0x7ff0000000000000ll);
 
     uint32_t alive_mask = 0, par_mask = 0;  // per lane, bit r: slot r holds a live path / its unit is buffer 1
     uint32_t cntpack = 0;                   // per slot 8 bits: survivors of the last scan (bit 7: list overflowed)
-    uint32_t n_samples = 0, n_casts = 0, n_exact = 0, n_black = 0, n_early = 0, n_primary = 0, n_ovf = 0;
+    uint32_t n_samples = 0, n_casts = 0, n_exact = 0, n_black = 0, n_early = 0, n_primary = 0, n_ovf = 0, n_nodes = 0;
+    Best pending[R];  // BVH mode: closest hit found by this round's traversal, consumed by the next advance
+#pragma unroll
+    for (int r = 0; r < R; ++r) { pending[r].t = 0.0; pending[r].C = 1.0; pending[r].k = -1; }
 
     Unit u0, u1;
     u0.valid = u1.valid = 0; u0.total = u0.next = u1.total = u1.next = 0; u0.tile_l = u1.tile_l = u0.chunk = u1.chunk = 0;
@@ -198,8 +204,12 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R>::kMinBlocks) render_
                 const bool ovf = ((cntpack >> (8 * r + 7)) & 1u) != 0;
                 ++n_casts;
                 if (ovf && a.scan_mode == 0) ++n_ovf;
-                const Best best = resolve_hits(a.sc, ovf, cnt, cand + r * kThreads, R * kThreads, ox, oy, oz, dx, dy, dz, A,
-                                               a.tmin, kInf, n_exact);
+                Best best = pending[0];
+#pragma unroll
+                for (int q = 1; q < R; ++q) if (r == q) best = pending[q];
+                if (!kBvh || ovf)
+                    best = resolve_hits(a.sc, ovf, cnt, cand + r * kThreads, R * kThreads, ox, oy, oz, dx, dy, dz, A, a.tmin,
+                                        kInf, n_exact);
                 if (best.k < 0) {
                     // miss: sky (programs/main.cc:46-48) * 0.5^bounces -> fixed-point accumulate
                     double cr, cg, cb;
@@ -322,21 +332,30 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R>::kMinBlocks) render_
             const double A = dx * dx + dy * dy + dz * dz;
             // a direction of length 0 / inf / NaN or a far-away origin is left to the sequential FP64 scan
             const bool sane = A > 0.0 && A < kInf && (ox * ox + oy * oy + oz * oz) < kCullMaxMag2;
-            f[r] = make_cull_ray(live && sane && a.scan_mode == 0, ox, oy, oz, dx, dy, dz, A);
             cnt[r] = 0;
-            ovf[r] = live && (a.scan_mode != 0 || !sane);
+            if (kBvh) {
+                ovf[r] = live && !(sane && a.tmin >= 0.0);  // such rays take the sequential FP64 scan
+                if (live && !ovf[r]) {
+                    bool deep = false;
+                    pending[r] = bvh_cast(a.sc, ox, oy, oz, dx, dy, dz, A, a.tmin, kInf, n_exact, n_nodes, deep);
+                    ovf[r] = deep;  // traversal stack exhausted (degenerate tree): sequential scan instead
+                }
+            } else {
+                f[r] = make_cull_ray(live && sane && a.scan_mode == 0, ox, oy, oz, dx, dy, dz, A);
+                ovf[r] = live && (a.scan_mode != 0 || !sane);
+            }
         }
-        if (a.scan_mode == 0) cull_scan<R, kConst>(s_filt, a.sc.npad, f, cand, kThreads, cnt, ovf);
+        if (!kBvh && a.scan_mode == 0) cull_scan<R, kConst>(s_filt, a.sc.npad, f, cand, kThreads, cnt, ovf);
         cntpack = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) cntpack |= ((uint32_t)cnt[r] | (ovf[r] ? 0x80u : 0u)) << (8 * r);
     }
 
     // ---------------- flush counters: warp-shuffle reduce, one atomic per warp and counter
-    uint32_t vals[7] = {n_samples, n_casts, n_exact, n_black, n_early, n_primary, n_ovf};
-    const int slots[7] = {ST_SAMPLES, ST_CASTS, ST_EXACT_TESTS, ST_BLACK, ST_EARLY_OUTS, ST_PRIMARY_HITS, ST_OVERFLOWS};
+    uint32_t vals[8] = {n_samples, n_casts, n_exact, n_black, n_early, n_primary, n_ovf, n_nodes};
+    const int slots[8] = {ST_SAMPLES, ST_CASTS, ST_EXACT_TESTS, ST_BLACK, ST_EARLY_OUTS, ST_PRIMARY_HITS, ST_OVERFLOWS, ST_NODE_TESTS};
 #pragma unroll
-    for (int c = 0; c < 7; ++c) {
+    for (int c = 0; c < 8; ++c) {
         unsigned long long v = vals[c];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -373,6 +392,18 @@ struct RayBatchArgs {
 __device__ __forceinline__ Best cast_one(const SceneDev& sc, const float4* s_filt, uint16_t* cand, int scan_mode,
                                          bool alive, double ox, double oy, double oz, double dx, double dy, double dz,
                                          double A, double tmin, double tmax, uint32_t& n_exact, uint32_t& n_ovf) {
+    if (scan_mode == 2) {  // flattened BVH
+        Best best;
+        best.t = tmax; best.C = 1.0; best.k = -1;
+        if (alive) {
+            const bool ok = A > 0.0 && A < __longlong_as_double(0x7ff0000000000000ll) && tmin >= 0.0;
+            bool deep = false;
+            uint32_t n_nodes = 0;
+            if (ok) best = bvh_cast(sc, ox, oy, oz, dx, dy, dz, A, tmin, tmax, n_exact, n_nodes, deep);
+            if (!ok || deep) { ++n_ovf; best = resolve_hits(sc, true, 0, cand, kThreads, ox, oy, oz, dx, dy, dz, A, tmin, tmax, n_exact); }
+        }
+        return best;
+    }
     CullRay f[1];
     int cnt[1] = {0};
     const bool sane = A > 0.0 && A < __longlong_as_double(0x7ff0000000000000ll) && (ox * ox + oy * oy + oz * oz) < kCullMaxMag2;

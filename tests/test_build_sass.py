@@ -26,7 +26,7 @@ def test_default_render_kernel_scans_on_the_uniform_datapath(rt):
     FFMA R, R, UR, R.  ptxas drops to vector LDC + three-register FFMAs (63% rate on B200, see
     tools/microbench.cu) for seemingly unrelated source changes -- e.g. a second __syncwarp() in the main
     loop or storing the loop counter -- so this is pinned here."""
-    s = _sass(rt, "_ZN2rt13render_kernelILi2ELb1EEEvNS_10RenderArgsE")
+    s = _sass(rt, "_ZN2rt13render_kernelILi2ELi1EEEvNS_10RenderArgsE")
     ldcu = len(re.findall(r"LDCU(\.\d+)? UR\d+, c\[0x3\]", s))
     ldc_vec = len(re.findall(r"LDC(\.\d+)? R\d+, c\[0x3\]\[R", s))
     ffma_ur = len(re.findall(r"FFMA R\d+, [^;]*UR\d+", s))
@@ -38,7 +38,7 @@ def test_default_render_kernel_scans_on_the_uniform_datapath(rt):
 
 
 def test_shared_memory_variant_stages_with_tma_bulk_copy(rt):
-    s = _sass(rt, "_ZN2rt13render_kernelILi2ELb0EEEvNS_10RenderArgsE")
+    s = _sass(rt, "_ZN2rt13render_kernelILi2ELi0EEEvNS_10RenderArgsE")
     assert "UBLKCP" in s                      # cp.async.bulk (TMA)
     assert "SYNCS.ARRIVE.TRANS64" in s        # mbarrier expect_tx
     assert "LDS.128" in s                     # float4 reads of the staged sphere array

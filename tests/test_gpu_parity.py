@@ -321,3 +321,85 @@ def test_dist_module_single_rank(rt, book):
         frame = rdist.render_sharded(sc, cam, p, 0, 1)
         torch.cuda.synchronize()
         assert np.array_equal(frame.cpu().numpy(), full)
+
+
+# ------------------------------------------------------------------ flattened BVH (RT_SCAN_BVH = 2)
+def _big_scene(grid_half):
+    from petershirleyraytracer_b200 import scenes
+    return scenes.book_scene(grid_half)
+
+
+@pytest.mark.parametrize("grid_half", [11, 35])
+def test_bvh_hit_matches_oracle(rt, grid_half):
+    """Closest hit through the BVH == the reference's list scan (index, t, p, normal bit for bit), including
+    the tmin=0 self-hit rays (origins exactly on spheres) and duplicate-sphere ties."""
+    c, r = _big_scene(grid_half)
+    rng = np.random.default_rng(grid_half)
+    n = 20000
+    k = rng.integers(0, len(r), size=n)
+    u = rng.normal(size=(n, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    org = c[k] + rng.choice([0.0, 1.0, 1.0, 2.0, 10.0], size=(n, 1)) * r[k][:, None] * u
+    org[::7] = [13.0, 2.0, 3.0]
+    d = rng.normal(size=(n, 3)) * rng.choice([1e-3, 1.0, 1.0, 100.0], size=(n, 1))
+    with rt.Scene(c, r) as sc:
+        idx, rec = rt.hit(sc, org, d, scan_mode=2)
+        # second bounce: origins are hit points produced by the path itself
+        m = idx >= 0
+        org2 = rec[m, 1:4]
+        d2 = rec[m, 4:7] + rng.uniform(-1, 1, size=(m.sum(), 3)) * 0.9
+        idx2, rec2 = rt.hit(sc, org2, d2, scan_mode=2)
+    oi, orec = ol.hit_batch("orc", c, r, org, d)
+    assert np.array_equal(idx, oi) and np.array_equal(bits(rec), bits(orec))
+    oi2, orec2 = ol.hit_batch("orc", c, r, org2, d2)
+    assert np.array_equal(idx2, oi2) and np.array_equal(bits(rec2), bits(orec2))
+    assert (oi2 >= 0).mean() > 0.5
+
+
+def test_bvh_ties_and_tiny_scenes(rt):
+    c = np.array([[0, 0, -3.0], [0, 0, -3.0], [5, 5, 5.0], [0, 0, -3.0], [0, 0, -3.0], [0, 0, -3.0], [1, 0, -3.0]])
+    r = np.array([1.0, 1.0, 0.5, 1.0, 1.0, 1.0, 0.25])
+    d = np.array([[0, 0, -1.0], [0.1, 0, -1.0], [0, 0.2, -1.0], [0, 0, 1.0], [1, 0, -3.0]])
+    with rt.Scene(c, r) as sc:
+        idx, rec = rt.hit(sc, np.zeros((5, 3)), d, scan_mode=2)
+    oi, orec = ol.hit_batch("orc", c, r, np.zeros((5, 3)), d)
+    assert list(idx) == list(oi) and idx[0] == 5
+    assert np.array_equal(bits(rec), bits(orec))
+    for n in (0, 1, 3):
+        with rt.Scene(c[:n], r[:n]) as sc:
+            idx, _ = rt.hit(sc, np.zeros((5, 3)), d, scan_mode=2)
+            oi, _ = ol.hit_batch("orc", c[:n], r[:n], np.zeros((5, 3)), d)
+            assert np.array_equal(idx, oi)
+
+
+def test_bvh_render_equals_linear_scan(rt, book):
+    from petershirleyraytracer_b200 import scenes
+    c, r = book
+    W, H, spp = 96, 64, 8
+    cam = scenes.book_camera(W, H)
+    base, bsum, bst = _render_both(rt, c, r, cam, W, H, spp, 50, 1, early_out=False)
+    img, s, st = _render_both(rt, c, r, cam, W, H, spp, 50, 1, early_out=False, scan_mode=2)
+    assert np.array_equal(img, base) and np.array_equal(bits(s), bits(bsum))
+    assert st["casts"] == bst["casts"] and st["black"] == bst["black"] and st["node_tests"] > 0
+
+
+def test_bvh_100k_spheres_config4(rt):
+    """BASELINE config 4 scene (~99.9k spheres): primary hits vs the oracle's list scan, and a small render vs
+    the FP64-everything mode."""
+    from petershirleyraytracer_b200 import scenes
+    c, r = _big_scene(158)
+    assert 99000 < len(r) < 101000
+    W, H = 96, 54
+    cam = scenes.book_camera(W, H)
+    with rt.Scene(c, r) as sc:
+        idx, t = rt.primary_hits(sc, cam, W, H, scan_mode=2)
+        p = rt.make_params(40, 24, 2, 50, seed=3, scan_mode=2)
+        cam2 = scenes.book_camera(40, 24)
+        a, asum, ast = rt.render(sc, cam2, p, want_sums=True)
+        p.scan_mode = 1
+        b, bsum, bst = rt.render(sc, cam2, p, want_sums=True)
+        auto, _, aust = rt.render(sc, cam2, rt.make_params(40, 24, 2, 50, seed=3))   # AUTO picks the BVH here
+    oi, ot = ol.primary_hits("orc", c, r, cam.as12(), W, H)
+    assert np.array_equal(idx, oi) and np.array_equal(bits(t), bits(ot))
+    assert np.array_equal(a, b) and np.array_equal(bits(asum), bits(bsum)) and ast["casts"] == bst["casts"]
+    assert np.array_equal(auto, a) and aust["node_tests"] > 0

@@ -32,3 +32,16 @@ if __name__ == "__main__":
     dc, dr = scenes.default_scene()
     run("c1", dc, dr, rt.Camera.default(), 400, 225, 100, early_out=False)
     run("c1", dc, dr, rt.Camera.default(), 400, 225, 100, early_out=True)
+    if "--c4" in sys.argv:
+        c4, r4 = scenes.book_scene(158)
+        cam4 = scenes.book_camera(1920, 1080)
+        for eo in (False, True):
+            with rt.Scene(c4, r4) as sc:
+                p = rt.make_params(1920, 1080, 8, 50, seed=1, early_out=eo)
+                rt.render(sc, cam4, p)
+                _, _, st = rt.render(sc, cam4, p)
+            print(json.dumps(dict(name="c4_bvh", early_out=eo, n=len(r4), ms=round(st["kernel_ms"], 2),
+                                  msamples_s=round(st["samples"] / st["kernel_ms"] / 1e3, 2),
+                                  casts_per_sample=round(st["casts"] / st["samples"], 3),
+                                  node_tests_per_cast=round(st["node_tests"] / st["casts"], 2),
+                                  exact_per_cast=round(st["exact_tests"] / st["casts"], 3), overflows=st["overflows"])), flush=True)
