@@ -184,8 +184,11 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     frame = torch.empty(H * W * 4, dtype=torch.uint8, device=dev)
 
-    def make(early_out):
-        return rt.make_params(W, H, spp, depth, seed=0, early_out=early_out, shard_rank=rank, shard_count=world)
+    def make(early_out, scan_mode=rt.SCAN_FILTERED):
+        # headline = the linear cull-scan kernel BASELINE.json's north_star specifies for this config; the
+        # library's AUTO mode (BVH traversal above 256 spheres) is timed too and reported under config
+        return rt.make_params(W, H, spp, depth, seed=0, early_out=early_out, scan_mode=scan_mode, shard_rank=rank,
+                              shard_count=world)
 
     layout = rt.tile_layout(make(False))
     shard = torch.empty(layout.shard_bytes, dtype=torch.uint8, device=dev) if world > 1 else None
@@ -245,6 +248,10 @@ def main():
     # ---- same frame with the exact early-out (bit-identical image, fewer casts)
     eo_ms, eo_kern_ms, _, eo_stats = timed(make(True), max(1, args.steps), 1)
     value_eo = samples_per_step * max(1, args.steps) / (eo_ms * 1e-3) / 1e6
+
+    # ---- the library's AUTO mode on the same frame (exact BVH traversal for this scene size)
+    auto_ms, _, _, auto_stats = timed(make(False, rt.SCAN_AUTO), max(1, args.steps), 1)
+    value_auto = samples_per_step * max(1, args.steps) / (auto_ms * 1e-3) / 1e6
 
     # ---- e2e: host buffers through the public C ABI (upload scene, render, read the frame back)
     e2e = None
@@ -318,8 +325,11 @@ def main():
         out = {"metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "f64 hit/shading + f32 cull", "data": "synthetic",
-               "config": config_dict(wl, args, extra={"early_out": False, "paths_per_lane": 2,
-                                                      "value_with_exact_early_out": value_eo}),
+               "config": config_dict(wl, args, extra={"early_out": False, "paths_per_lane": 2, "scan_mode": "linear cull scan (RT_SCAN_FILTERED)",
+                                                      "value_with_exact_early_out": value_eo,
+                                                      "value_auto_mode_bvh": value_auto,
+                                                      "auto_mode_node_tests_per_cast": None if not auto_stats else
+                                                      auto_stats["node_tests"] / max(1, auto_stats["casts"])}),
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(out), flush=True)
     scene.close()

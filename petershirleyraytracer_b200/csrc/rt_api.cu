@@ -104,7 +104,8 @@ void tile_layout(const rt_params* p, rt_tile_layout* L) {
 // AUTO -> FILTERED while the cull array fits in shared memory (the BVH path takes over above that).
 int resolve_scan_mode(const rt_scene* sc, int mode, int* out) {
     // AUTO: the linear cull scan while it is cheaper than a traversal, the BVH for large scenes
-    if (mode == RT_SCAN_AUTO) mode = (sc->cull_ok && sc->n <= 1024) ? RT_SCAN_FILTERED : RT_SCAN_BVH;
+    // (measured crossover on B200: ~200 spheres, tools/mode_compare.py)
+    if (mode == RT_SCAN_AUTO) mode = (!sc->cull_ok) ? RT_SCAN_EXACT : (sc->n <= 256 ? RT_SCAN_FILTERED : RT_SCAN_BVH);
     if (mode == RT_SCAN_FILTERED && !sc->cull_ok)
         return fail(RT_ERR_UNSUPPORTED, "scene has non-finite or huge (>1e15) coordinates: use RT_SCAN_EXACT");
     if (mode == RT_SCAN_BVH && !sc->d_bvh_nodes)

@@ -351,6 +351,8 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
                                          uint32_t& n_nodes, bool& overflow) {
     Best best;
     best.t = tmax; best.C = 1.0; best.k = -1;
+    // (An FP32 line test per leaf sphere before the FP64 test was measured: exact tests/cast 4.96 -> 1.21,
+    //  but 6 % slower overall -- the per-cast cull constants cost more than the FP64 tests they save.)
     const float kUp = 1.0f + 1.9073486328125e-06f, kDn = 1.0f - 1.9073486328125e-06f;  // 1 +- 2^-19
     const float fx = (float)ox, fy = (float)oy, fz = (float)oz;
     const float padx = fabsf(fx) * 2.384185791015625e-07f + 1e-37f, pady = fabsf(fy) * 2.384185791015625e-07f + 1e-37f,

@@ -165,6 +165,7 @@ def test_ray_color_vs_oracle_philox(rt, book, default_scene, mode, early_out):
 
 # ------------------------------------------------------------------ the render kernel
 def _render_both(rt, c, r, cam, W, H, spp, depth, seed, **kw):
+    kw.setdefault("scan_mode", 0)   # the linear cull scan unless a test asks for EXACT (1) / BVH (2) / AUTO (3)
     with rt.Scene(c, r) as sc:
         p = rt.make_params(W, H, spp, depth, seed=seed, **kw)
         rgba, sums, st = rt.render(sc, cam, p, want_sums=True)
@@ -210,7 +211,8 @@ def test_render_modes_agree_bitwise(rt, book):
     W, H, spp = 96, 64, 8
     cam = scenes.book_camera(W, H)
     base, bsum, _ = _render_both(rt, c, r, cam, W, H, spp, 50, 1)
-    for kw in (dict(scan_mode=1), dict(early_out=False), dict(paths_per_lane=1), dict(scan_mode=1, early_out=False),
+    for kw in (dict(scan_mode=1), dict(scan_mode=2), dict(scan_mode=3), dict(early_out=False), dict(paths_per_lane=1),
+               dict(scan_mode=1, early_out=False),
                dict(chunks=1), dict(chunks=3), dict(chunks=8), dict(chunks=5, paths_per_lane=1),
                dict(cull_smem=True), dict(cull_smem=True, paths_per_lane=1, chunks=2)):
         img, s, _ = _render_both(rt, c, r, cam, W, H, spp, 50, 1, **kw)
