@@ -5,6 +5,7 @@
 #include "rt_kernels.cuh"
 
 #include <cmath>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -73,6 +74,14 @@ struct rt_scene {
 };
 
 namespace {
+
+// The cull array of the scene being rendered lives in the (per-device) constant bank.  Renders issued on
+// different streams of one device are therefore chained: the copy into the bank waits for the previous
+// constant-bank render on that device.
+struct ConstBankGuard {
+    std::mutex mu;
+    cudaEvent_t last[64] = {};
+} g_const_bank;
 
 float round_down_f32(double v) {
     float f = (float)v;
@@ -167,6 +176,9 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     // TMA-staged shared-memory copy (reserved[2] == 1), kept for A/B evidence
     const bool use_const = p->reserved[2] != 1 && mode == RT_SCAN_FILTERED;
     if (use_const) {
+        std::lock_guard<std::mutex> lock(g_const_bank.mu);
+        cudaEvent_t& prev = g_const_bank.last[sc->device & 63];
+        if (prev) RT_CUDA(cudaStreamWaitEvent(stream, prev, 0));
         RT_CUDA(cudaMemcpyToSymbolAsync(rt::c_filt, sc->d_filt, (size_t)(sc->npad + rt::kScanPad) * sizeof(float4), 0,
                                         cudaMemcpyDeviceToDevice, stream));
     }
@@ -213,6 +225,12 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     kern<<<grid, rt::kThreads, S.total, stream>>>(a);
     RT_CUDA(cudaGetLastError());
     RT_CUDA(cudaEventRecord(sc->ev1, stream));
+    if (use_const) {
+        std::lock_guard<std::mutex> lock(g_const_bank.mu);
+        cudaEvent_t& prev = g_const_bank.last[sc->device & 63];
+        if (!prev) RT_CUDA(cudaEventCreateWithFlags(&prev, cudaEventDisableTiming));
+        RT_CUDA(cudaEventRecord(prev, stream));
+    }
     sc->pending = true; sc->last_stream = stream; sc->last_mode = mode; sc->last_launches = 1;
     return RT_OK;
 }
