@@ -6,6 +6,7 @@ from petershirleyraytracer_b200 import scenes
 
 def run(name, c, r, cam, W, H, spp, **kw):
     with rt.Scene(c, r) as sc:
+        kw.setdefault("scan_mode", 0)
         p = rt.make_params(W, H, spp, 50, seed=1, **kw)
         rt.render(sc, cam, p)  # warm-up
         _, _, st = rt.render(sc, cam, p)
@@ -25,7 +26,7 @@ if __name__ == "__main__":
     c, r = scenes.book_scene(11)
     cam = scenes.book_camera(1200, 800)
     for smem in (False, True):
-        for ppl in (1, 2, 4):
+        for ppl in (2, 3):
             for eo in (False,):
                 o = run("c3", c, r, cam, 1200, 800, spp, early_out=eo, paths_per_lane=ppl, cull_smem=smem)
                 print("   frac_of_peak(11 slots/test) =", round(o["gtests_s"] * 1e9 * 11 / peak, 4))
