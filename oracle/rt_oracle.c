@@ -104,21 +104,37 @@ static inline v3 cube21(uint32_t fx, uint32_t fy, uint32_t fz) {
                    -1.0 + (1.0 - -1.0) * ((double)fz * s21));
 }
 
-/* programs/vec3.h:83-95: reject only if len^2 > 1 */
+/* programs/vec3.h:83-95: reject only if len^2 > 1.  PHILOX mode: one block per bounce gives tries A and B;
+ * bounces that reject both continue with xorshift128 seeded by the block's words, three outputs per try. */
 static inline v3 random_in_unit_sphere(rng_t* g) {
-    for (;;) {
-        if (g->mode == ORC_RNG_RAND15) {
+    if (g->mode == ORC_RNG_RAND15) {
+        for (;;) {
             v3 v = rng_cube15(g);
             if (v3_len2(v) > 1.0) continue;
             return v;
         }
-        uint32_t w[4];
-        rng_philox_block(g, w);
-        v3 a = cube21(w[0] >> 11, w[1] >> 11, w[2] >> 11);
-        if (!(v3_len2(a) > 1.0)) return a;
-        v3 b = cube21(((w[0] & 0x7ffu) << 10) | (w[3] >> 22), ((w[1] & 0x7ffu) << 10) | ((w[3] >> 12) & 0x3ffu),
-                      ((w[2] & 0x7ffu) << 10) | ((w[3] >> 2) & 0x3ffu));
-        if (!(v3_len2(b) > 1.0)) return b;
+    }
+    uint32_t w[4];
+    rng_philox_block(g, w);
+    v3 a = cube21(w[0] >> 11, w[1] >> 11, w[2] >> 11);
+    if (!(v3_len2(a) > 1.0)) return a;
+    v3 b = cube21(((w[0] & 0x7ffu) << 10) | (w[3] >> 22), ((w[1] & 0x7ffu) << 10) | ((w[3] >> 12) & 0x3ffu),
+                  ((w[2] & 0x7ffu) << 10) | ((w[3] >> 2) & 0x3ffu));
+    if (!(v3_len2(b) > 1.0)) return b;
+    uint32_t x0 = w[0], x1 = w[1], x2 = w[2], x3 = w[3];
+    if ((x0 | x1 | x2 | x3) == 0u) x0 = 1u;
+    for (;;) {
+        uint32_t f[3];
+        for (int i = 0; i < 3; ++i) {
+            uint32_t t = x3;
+            const uint32_t s0 = x0;
+            x3 = x2; x2 = x1; x1 = s0;
+            t ^= t << 11; t ^= t >> 8;
+            x0 = t ^ s0 ^ (s0 >> 19);
+            f[i] = x0 >> 11;
+        }
+        v3 c = cube21(f[0], f[1], f[2]);
+        if (!(v3_len2(c) > 1.0)) return c;
     }
 }
 /* programs/vec3.h:102-109: keep if dot > 0, else negate (dot == 0 negates) */

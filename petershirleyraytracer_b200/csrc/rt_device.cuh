@@ -454,19 +454,37 @@ __device__ __forceinline__ bool cube_try(uint32_t fx, uint32_t fy, uint32_t fz, 
     return !(l2 > 1.0);
 }
 
-// programs/vec3.h:83-109 random_in_hemisphere driven by Philox blocks.  Every block carries TWO tries of
-// the rejection loop as six 21-bit uniforms (the reference's rand() has 15 bits): try A = top 21 bits of
-// words 0,1,2; try B = the low 11 bits of words 0,1,2 extended by 10-bit fields of word 3.
+// programs/vec3.h:83-109 random_in_hemisphere.  One Philox block per bounce: it carries the first TWO tries of
+// the rejection loop as six 21-bit uniforms (the reference's rand() has 15 bits): try A = top 21 bits of words
+// 0,1,2; try B = the low 11 bits of words 0,1,2 extended by 10-bit fields of word 3.  The 5 % of bounces that
+// reject both continue with xorshift128 (Marsaglia 2003) seeded by the block's four words, three outputs per
+// try (top 21 bits each): a cheap continuation instead of further 10-round blocks, since the warp runs as many
+// loop iterations as its unluckiest lane.
 __device__ __forceinline__ void random_in_hemisphere(uint32_t pix, uint32_t smp, uint32_t& blk, uint32_t k0, uint32_t k1,
                                                      double nx, double ny, double nz, double& rx, double& ry,
                                                      double& rz) {
-    for (;;) {
-        const uint4 w = philox4x32_10(pix, smp, blk, 0u, k0, k1);
-        ++blk;
-        if (cube_try(w.x >> 11, w.y >> 11, w.z >> 11, rx, ry, rz)) break;
-        if (cube_try(((w.x & 0x7ffu) << 10) | (w.w >> 22), ((w.y & 0x7ffu) << 10) | ((w.w >> 12) & 0x3ffu),
-                     ((w.z & 0x7ffu) << 10) | ((w.w >> 2) & 0x3ffu), rx, ry, rz))
-            break;
+    const uint4 w = philox4x32_10(pix, smp, blk, 0u, k0, k1);
+    ++blk;
+    bool ok = cube_try(w.x >> 11, w.y >> 11, w.z >> 11, rx, ry, rz);
+    if (!ok)
+        ok = cube_try(((w.x & 0x7ffu) << 10) | (w.w >> 22), ((w.y & 0x7ffu) << 10) | ((w.w >> 12) & 0x3ffu),
+                      ((w.z & 0x7ffu) << 10) | ((w.w >> 2) & 0x3ffu), rx, ry, rz);
+    if (!ok) {
+        uint32_t x0 = w.x, x1 = w.y, x2 = w.z, x3 = w.w;
+        if ((x0 | x1 | x2 | x3) == 0u) x0 = 1u;
+        do {
+            uint32_t f[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                uint32_t t = x3;
+                const uint32_t s0 = x0;
+                x3 = x2; x2 = x1; x1 = s0;
+                t ^= t << 11; t ^= t >> 8;
+                x0 = t ^ s0 ^ (s0 >> 19);
+                f[i] = x0 >> 11;
+            }
+            ok = cube_try(f[0], f[1], f[2], rx, ry, rz);
+        } while (!ok);
     }
     if (!(ddot(rx, ry, rz, nx, ny, nz) > 0)) { rx = -rx; ry = -ry; rz = -rz; }  // programs/vec3.h:105-108
 }
