@@ -150,6 +150,12 @@ int rt_philox(const uint32_t* ctr4, const uint32_t* key2, int32_t nblocks, int32
  * FMA/s) measured with a register-resident FFMA loop; the denominator of the FP32 roofline. */
 int rt_measure_fp32_peak(int32_t device, double* fma_per_s_out, double* ms_out);
 
+/* Self-check: the hit distance t = num / A (programs/sphere.cc:24,29) is computed from one reciprocal per cast
+ * plus two exact-residual corrections (DESIGN.md "division"); this compares that form with the IEEE division on n
+ * pseudo-random operand pairs (all exponent ranges, zeros, denormals, infinities) and returns the number of
+ * pairs whose quotients differ in any bit (must be 0). */
+int rt_check_division(int32_t device, uint64_t n, uint64_t seed, uint64_t* mismatches_out);
+
 int rt_device_info(int32_t device, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, char* name, int32_t name_cap);
 
 #ifdef __cplusplus

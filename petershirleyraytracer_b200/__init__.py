@@ -24,6 +24,7 @@ ABI_SYMBOLS = [
     "rt_abi_version", "rt_last_error", "rt_upload_scene", "rt_free_scene", "rt_scene_size", "rt_render",
     "rt_render_device", "rt_render_finish", "rt_get_tile_layout", "rt_deinterleave", "rt_primary_hits", "rt_hit",
     "rt_ray_color", "rt_write_color", "rt_get_ray", "rt_philox", "rt_measure_fp32_peak", "rt_device_info",
+    "rt_check_division",
 ]
 
 
@@ -89,6 +90,7 @@ def lib() -> C.CDLL:
     L.rt_philox.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int32, C.c_int32, C.POINTER(C.c_uint32)]
     L.rt_measure_fp32_peak.argtypes = [C.c_int32, dp, dp]
     L.rt_device_info.argtypes = [C.c_int32, ip, ip, ip, C.c_char_p, C.c_int32]
+    L.rt_check_division.argtypes = [C.c_int32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
     _lib = L
     return L
 
@@ -302,6 +304,13 @@ def measure_fp32_peak(device: int = 0) -> tuple[float, float]:
     f, ms = C.c_double(), C.c_double()
     _check(lib().rt_measure_fp32_peak(device, C.byref(f), C.byref(ms)))
     return f.value, ms.value
+
+
+def check_division(n: int, seed: int = 1, device: int = 0) -> int:
+    """Mismatches between the short hit-distance division and __ddiv_rn on n random operand pairs (must be 0)."""
+    bad = C.c_uint64()
+    _check(lib().rt_check_division(device, n, seed, C.byref(bad)))
+    return bad.value
 
 
 def device_info(device: int = 0) -> dict:

@@ -56,6 +56,7 @@ struct rt_scene {
     bool cull_ok = true;   // every sphere finite and of moderate magnitude: the FP32 cull is usable
     float4* d_filt = nullptr;
     double4* d_exact = nullptr;
+    double* d_inv_r = nullptr;        // RN(1/r) per sphere
     float4* d_bvh_nodes = nullptr;    // flattened BVH (rt_bvh.h), built at upload
     int32_t* d_bvh_leaf = nullptr;
     int bvh_nodes = 0;
@@ -127,7 +128,7 @@ int resolve_scan_mode(const rt_scene* sc, int mode, int* out) {
 
 rt::SceneDev scene_dev(const rt_scene* sc, int mode) {
     rt::SceneDev d;
-    d.filt = sc->d_filt; d.exact = sc->d_exact; d.n = sc->n;
+    d.filt = sc->d_filt; d.exact = sc->d_exact; d.inv_r = sc->d_inv_r; d.n = sc->n;
     d.npad = (mode == RT_SCAN_FILTERED) ? sc->npad : 0;  // EXACT / BVH stage nothing
     d.bvh_nodes = sc->d_bvh_nodes; d.bvh_leaf = sc->d_bvh_leaf;
     return d;
@@ -297,6 +298,7 @@ int rt_upload_scene(const double* centres_xyz, const double* radii, int32_t n, i
     // FP32 cull entries {c, |c|^2 - r^2 - E_k}: computed in FP64, constant term rounded DOWN.
     std::vector<float4> filt((size_t)sc->npad + rt::kScanPad);
     std::vector<double4> exact((size_t)n > 0 ? n : 1);
+    std::vector<double> inv_r((size_t)n > 0 ? n : 1);
     for (int k = 0; k < sc->npad + rt::kScanPad; ++k) {
         float4 f;
         if (k < n) {
@@ -307,6 +309,7 @@ int rt_upload_scene(const double* centres_xyz, const double* radii, int32_t n, i
             f.w = round_down_f32(a2 - r2 - Ek);
             if (!(a2 < rt::kCullMaxMag2) || !(r2 < rt::kCullMaxMag2)) sc->cull_ok = false;  // also catches NaN / inf
             exact[k] = make_double4(cx, cy, cz, r);
+            inv_r[k] = 1.0 / r;  // IEEE double division on the host == __ddiv_rn(1.0, r)
         } else {
             f.x = f.y = f.z = 0.f;
             f.w = INFINITY;  // q = +inf -> D = -inf: never passes
@@ -317,10 +320,12 @@ int rt_upload_scene(const double* centres_xyz, const double* radii, int32_t n, i
     do {
         if (cudaMalloc(&sc->d_filt, filt.size() * sizeof(float4)) != cudaSuccess ||
             cudaMalloc(&sc->d_exact, exact.size() * sizeof(double4)) != cudaSuccess ||
+            cudaMalloc(&sc->d_inv_r, inv_r.size() * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&sc->d_tile_counter, sizeof(unsigned int)) != cudaSuccess ||
             cudaMalloc(&sc->d_stats, rt::kNumStats * sizeof(unsigned long long)) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
         if (cudaMemcpy(sc->d_filt, filt.data(), filt.size() * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess ||
-            cudaMemcpy(sc->d_exact, exact.data(), exact.size() * sizeof(double4), cudaMemcpyHostToDevice) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
+            cudaMemcpy(sc->d_exact, exact.data(), exact.size() * sizeof(double4), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(sc->d_inv_r, inv_r.data(), inv_r.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
         if (cudaEventCreate(&sc->ev0) != cudaSuccess || cudaEventCreate(&sc->ev1) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
         // flattened BVH (exact closest-hit semantics, rt_bvh.h); finite scenes only
         if (sc->cull_ok) {
@@ -347,7 +352,7 @@ void rt_free_scene(rt_scene* sc) {
     if (!sc) return;
     DeviceGuard guard(sc->device);
     if (sc->pending) cudaEventSynchronize(sc->ev1);
-    cudaFree(sc->d_filt); cudaFree(sc->d_exact); cudaFree(sc->d_tile_counter); cudaFree(sc->d_stats);
+    cudaFree(sc->d_filt); cudaFree(sc->d_exact); cudaFree(sc->d_inv_r); cudaFree(sc->d_tile_counter); cudaFree(sc->d_stats);
     cudaFree(sc->d_bvh_nodes); cudaFree(sc->d_bvh_leaf);
     cudaFree(sc->d_frame); cudaFree(sc->d_sum); cudaFree(sc->d_accum);
     if (sc->ev0) cudaEventDestroy(sc->ev0);
@@ -572,6 +577,21 @@ int rt_philox(const uint32_t* ctr4, const uint32_t* key2, int32_t nblocks, int32
     rt::philox_kernel<<<(nblocks + 255) / 256 > 1024 ? 1024 : (nblocks + 255) / 256, 256>>>(d_ctr.p, d_key.p, nblocks, d_out.p);
     RT_CUDA(cudaGetLastError());
     RT_CUDA(cudaMemcpy(out4, d_out.p, 4 * (size_t)nblocks * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_check_division(int32_t device, uint64_t n, uint64_t seed, uint64_t* mismatches_out) {
+    if (!mismatches_out) return fail(RT_ERR_INVALID, "NULL out");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    DevBuf<unsigned long long> d_bad;
+    RT_CUDA(d_bad.alloc(1));
+    RT_CUDA(cudaMemset(d_bad.p, 0, sizeof(unsigned long long)));
+    rt::div_check_kernel<<<1184, 256>>>((unsigned long long)n, (unsigned long long)seed, d_bad.p);
+    RT_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    RT_CUDA(cudaMemcpy(&h, d_bad.p, sizeof h, cudaMemcpyDeviceToHost));
+    *mismatches_out = h;
     return RT_OK;
 }
 

@@ -42,19 +42,37 @@ __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a,
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 __device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
-// num / A for the hit distance (programs/sphere.cc:24,29).  With tmin = 0 about half of all hits are
-// self-hits whose numerator is exactly +-0; IEEE gives +-0 / A = +-0 for finite A > 0,
-// so that case is answered directly instead of through the division's special-operand subroutine.
-__device__ __forceinline__ double ddiv_t(double num, double A) {
-    const bool zero_num = num == 0.0 && A > 0.0 && A < __longlong_as_double(0x7ff0000000000000ll);
-    // The division is evaluated for every lane (the compiler if-converts it), so a zero numerator is
-    // replaced by 1.0 to keep those lanes off the special-operand subroutine; their quotient is discarded.
-    // The empty asm hides the substitution from the optimiser, which otherwise proves the quotient unused
-    // for those lanes and feeds the zero straight back into the division.
-    double safe = zero_num ? 1.0 : num;
-    asm volatile("" : "+d"(safe));
-    const double q = __ddiv_rn(safe, A);
-    return zero_num ? num : q;
+// num / A for the hit distance (programs/sphere.cc:24,29), correctly rounded (== __ddiv_rn) but cheap.
+// All candidates of a cast divide by the same A = dot(dir, dir), so the cast computes rA = RN(1/A) once
+// (RcpA) and every quotient is  q0 = RN(num*rA); q1 = RN(q0 + (num - A*q0)*rA); q = RN(q1 + (num - A*q1)*rA)
+// with the residuals exact in one FMA each.  q1 is a faithful rounding of num/A (|q1 - num/A| <= half an ulp
+// plus 1.5 ulp * 2^-53), so by Markstein's theorem (Muller et al., Handbook of Floating-Point Arithmetic,
+// "division by Newton-Raphson": y = RN(1/b), q faithful, r = a - b*q exact => RN(q + r*y) = RN(a/b)) the last
+// step is the IEEE quotient.  The theorem needs no over/underflow, so the short form is used only when the
+// exponents of A and num are moderate; everything else takes __ddiv_rn.  (tools/div_check.c compares the two on
+// 4e8 random and adversarial operand pairs.)  With tmin = 0 about half of all hits are self-hits whose
+// numerator is exactly +-0: +-0 / A = +-0 for finite A > 0 is answered directly.
+struct RcpA {
+    double A, rA;
+    bool fast;  // 2^-200 < A < 2^200: the short division is valid for moderate numerators
+};
+__device__ __forceinline__ RcpA make_rcp(double A) {
+    RcpA d;
+    d.A = A;
+    const int e = (__double2hiint(A) >> 20) & 0x7ff;   // sign bit excluded; A <= 0, inf, NaN fail the range test
+    d.fast = A > 0.0 && e > 1023 - 200 && e < 1023 + 200;
+    d.rA = __drcp_rn(d.fast ? A : 1.0);
+    return d;
+}
+__device__ __forceinline__ double ddiv_t(double num, const RcpA& d) {
+    const int e = (__double2hiint(num) >> 20) & 0x7ff;
+    const bool zero = num == 0.0;
+    // the short form runs for every lane (no branch); only operands outside its range take the subroutine
+    const double q0 = __dmul_rn(num, d.rA);
+    const double q1 = __fma_rn(__fma_rn(-d.A, q0, num), d.rA, q0);
+    double q = __fma_rn(__fma_rn(-d.A, q1, num), d.rA, q1);
+    if (!(d.fast && (zero || (e > 1023 - 700 && e < 1023 + 700)))) q = __ddiv_rn(num, d.A);
+    return (zero && d.fast) ? num : q;  // +-0 / A = +-0 (the short form would lose the sign of -0)
 }
 // programs/vec3.h:156-159: (u0*v0 + u1*v1) + u2*v2
 __device__ __forceinline__ double ddot(double ax, double ay, double az, double bx, double by, double bz) {
@@ -82,6 +100,7 @@ __device__ __forceinline__ double u32_unit(uint32_t w) { return dmul((double)w, 
 struct SceneDev {
     const float4* filt;    // npad entries {cx, cy, cz, |c|^2 - r^2 - E_k} (FP32 cull), padded with never-pass entries
     const double4* exact;  // n entries {cx, cy, cz, r} (FP64, list order)
+    const double* inv_r;   // n entries RN(1.0 / r): the reciprocal of programs/vec3.h:151-154, tabulated at upload
     int n, npad;
     const float4* bvh_nodes;   // 4 float4 per node (rt_bvh.h: BvhNode), root = node 0; NULL if not built
     const int32_t* bvh_leaf;   // sphere list indices, leaf by leaf
@@ -243,15 +262,20 @@ __device__ __forceinline__ void cull_scan(const float4* __restrict__ s_filt, int
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (m[r] < f[r].o2) continue;
+                // 12-bit pass mask without branches (one compare + one select per entry), then one loop over
+                // the set bits (list order).  The straightforward "if (pass) append" per entry compiles to 24
+                // tiny divergent regions per step, which held 16 % of the kernel's warp-state samples.
+                uint32_t pm = 0u;
 #pragma unroll
-                for (int u = 0; u < kScanStep; ++u) {
-                    if (!(D[r][u] < f[r].o2)) {
-                        if (cnt[r] < kCandCap) {
-                            cand[(cnt[r] * R + r) * stride] = (uint16_t)(kv + u);
-                            ++cnt[r];
-                        } else {
-                            ovf[r] = true;
-                        }
+                for (int u = 0; u < kScanStep; ++u) pm |= (D[r][u] < f[r].o2) ? 0u : (1u << u);
+                while (pm) {
+                    const int u = __ffs((int)pm) - 1;
+                    pm &= pm - 1u;
+                    if (cnt[r] < kCandCap) {
+                        cand[(cnt[r] * R + r) * stride] = (uint16_t)(kv + u);
+                        ++cnt[r];
+                    } else {
+                        ovf[r] = true;
                     }
                 }
             }
@@ -270,7 +294,8 @@ struct Best {
 // the caller's record (t, k) is replaced, which is hittable_list.cc:13-15.  The hit record itself
 // (p, normal) is only needed for the final winner and is built by make_record().
 __device__ __forceinline__ void exact_test(const double4* __restrict__ exact, int k, double ox, double oy, double oz,
-                                           double dx, double dy, double dz, double A, double tmin, Best& best) {
+                                           double dx, double dy, double dz, const RcpA& dA, double tmin, Best& best) {
+    const double A = dA.A;
     const double2 c01 = __ldg(reinterpret_cast<const double2*>(exact + k));
     const double2 c23 = __ldg(reinterpret_cast<const double2*>(exact + k) + 1);
     const double amx = dsub(ox, c01.x), amy = dsub(oy, c01.y), amz = dsub(oz, c23.x);  // sphere.cc:7
@@ -279,9 +304,9 @@ __device__ __forceinline__ void exact_test(const double4* __restrict__ exact, in
     const double disc = dsub(dmul(HALF_B, HALF_B), dmul(A, C));                         // sphere.cc:14
     if (disc < 0) return;                                                                // sphere.cc:15-18
     const double sqrt_d = dsqrt(disc);
-    double t = ddiv_t(dsub(-HALF_B, sqrt_d), A);  // sphere.cc:24
-    if (t < tmin || t > best.t) {               // sphere.cc:26 (closed interval)
-        t = ddiv_t(dadd(-HALF_B, sqrt_d), A);   // sphere.cc:29
+    double t = ddiv_t(dsub(-HALF_B, sqrt_d), dA);  // sphere.cc:24
+    if (t < tmin || t > best.t) {                // sphere.cc:26 (closed interval)
+        t = ddiv_t(dadd(-HALF_B, sqrt_d), dA);   // sphere.cc:29
         if (t < tmin || t > best.t) return;     // sphere.cc:30-31
     }
     best.t = t; best.C = C; best.k = k;
@@ -293,15 +318,15 @@ struct Record {  // programs/hittable.h:7-13
 };
 
 // programs/sphere.cc:34-36 + programs/hittable.h:14-18 for the kept hit
-__device__ __forceinline__ Record make_record(const double4* __restrict__ exact, const Best& best, double ox, double oy,
+__device__ __forceinline__ Record make_record(const SceneDev& sc, const Best& best, double ox, double oy,
                                               double oz, double dx, double dy, double dz) {
-    const double2 c01 = __ldg(reinterpret_cast<const double2*>(exact + best.k));
-    const double2 c23 = __ldg(reinterpret_cast<const double2*>(exact + best.k) + 1);
+    const double2 c01 = __ldg(reinterpret_cast<const double2*>(sc.exact + best.k));
+    const double2 c23 = __ldg(reinterpret_cast<const double2*>(sc.exact + best.k) + 1);
     Record rec;
     rec.px = dadd(ox, dmul(best.t, dx));  // programs/ray.h:27 orig + t*dir
     rec.py = dadd(oy, dmul(best.t, dy));
     rec.pz = dadd(oz, dmul(best.t, dz));
-    const double inv_r = ddiv(1.0, c23.y);  // programs/vec3.h:151-154: (1/t) * v
+    const double inv_r = __ldg(sc.inv_r + best.k);  // programs/vec3.h:151-154: (1/t) * v, 1/r tabulated (same IEEE quotient)
     const double wx = dmul(inv_r, dsub(rec.px, c01.x));
     const double wy = dmul(inv_r, dsub(rec.py, c01.y));
     const double wz = dmul(inv_r, dsub(rec.pz, c23.x));
@@ -318,8 +343,9 @@ __device__ __forceinline__ Record make_record(const double4* __restrict__ exact,
 // whose near root lies beyond closest_so_far is rejected either way.)  Used by the BVH traversal, which
 // meets spheres in tree order.
 __device__ __forceinline__ bool exact_test_unordered(const double4* __restrict__ exact, int k, double ox, double oy,
-                                                     double oz, double dx, double dy, double dz, double A, double tmin,
-                                                     double tmax, Best& best) {
+                                                     double oz, double dx, double dy, double dz, const RcpA& dA,
+                                                     double tmin, double tmax, Best& best) {
+    const double A = dA.A;
     const double2 c01 = __ldg(reinterpret_cast<const double2*>(exact + k));
     const double2 c23 = __ldg(reinterpret_cast<const double2*>(exact + k) + 1);
     const double amx = dsub(ox, c01.x), amy = dsub(oy, c01.y), amz = dsub(oz, c23.x);
@@ -328,9 +354,9 @@ __device__ __forceinline__ bool exact_test_unordered(const double4* __restrict__
     const double disc = dsub(dmul(HALF_B, HALF_B), dmul(A, C));
     if (disc < 0) return false;
     const double sqrt_d = dsqrt(disc);
-    double t = ddiv_t(dsub(-HALF_B, sqrt_d), A);
+    double t = ddiv_t(dsub(-HALF_B, sqrt_d), dA);
     if (t < tmin || t > tmax) {
-        t = ddiv_t(dadd(-HALF_B, sqrt_d), A);
+        t = ddiv_t(dadd(-HALF_B, sqrt_d), dA);
         if (t < tmin || t > tmax) return false;
     }
     if (best.k < 0 || t < best.t || (t == best.t && k > best.k)) {
@@ -351,6 +377,7 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
                                          uint32_t& n_nodes, bool& overflow) {
     Best best;
     best.t = tmax; best.C = 1.0; best.k = -1;
+    const RcpA dA = make_rcp(A);
     // (An FP32 line test per leaf sphere before the FP64 test was measured: exact tests/cast 4.96 -> 1.21,
     //  but 6 % slower overall -- the per-cast cull constants cost more than the FP64 tests they save.)
     const float kUp = 1.0f + 1.9073486328125e-06f, kDn = 1.0f - 1.9073486328125e-06f;  // 1 +- 2^-19
@@ -400,7 +427,7 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
                 for (int i = 0; i < count; ++i) {
                     const int k = __ldg(sc.bvh_leaf + first + i);
                     ++n_exact;
-                    if (exact_test_unordered(sc.exact, k, ox, oy, oz, dx, dy, dz, A, tmin, tmax, best))
+                    if (exact_test_unordered(sc.exact, k, ox, oy, oz, dx, dy, dz, dA, tmin, tmax, best))
                         best_up = __double2float_ru(best.t);
                 }
             }
@@ -434,10 +461,11 @@ __device__ __forceinline__ Best resolve_hits(const SceneDev& sc, bool ovf, int c
     Best best;
     best.t = tmax; best.C = 1.0; best.k = -1;
     const int n_iter = ovf ? sc.n : cnt;  // candidate list, or every sphere when the list overflowed
+    const RcpA dA = make_rcp(A);
 #pragma unroll 1
     for (int e = 0; e < n_iter; ++e) {
         const int k = ovf ? e : (int)cand[e * cand_step];
-        if (k < sc.n) exact_test(sc.exact, k, ox, oy, oz, dx, dy, dz, A, tmin, best);
+        if (k < sc.n) exact_test(sc.exact, k, ox, oy, oz, dx, dy, dz, dA, tmin, best);
     }
     n_exact += (uint32_t)n_iter;
     return best;

@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R>::kMinBlocks) render_
                         ++n_early; ++n_black;
                         alive_mask &= ~bit;
                     } else {
-                        const Record rec = make_record(a.sc.exact, best, ox, oy, oz, dx, dy, dz);
+                        const Record rec = make_record(a.sc, best, ox, oy, oz, dx, dy, dz);
                         double rx, ry, rz;
                         random_in_hemisphere(m.x, m.y, m.z, a.key0, a.key1, rec.nx, rec.ny, rec.nz, rx, ry, rz);
                         // programs/main.cc:42-43: target = (p + normal) + rv; next ray = (p, target - p)
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(kThreads) hit_kernel(const __grid_constant__ R
         } else {
             double* o = a.rec_out + 8 * (size_t)q;
             if (best.k >= 0) {
-                const Record rec = make_record(a.sc.exact, best, ox, oy, oz, dx, dy, dz);
+                const Record rec = make_record(a.sc, best, ox, oy, oz, dx, dy, dz);
                 o[0] = best.t; o[1] = rec.px; o[2] = rec.py; o[3] = rec.pz;
                 o[4] = rec.nx; o[5] = rec.ny; o[6] = rec.nz; o[7] = rec.front_face ? 1.0 : 0.0;
             } else {
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(kThreads) ray_color_kernel(const __grid_consta
             if (best.k < 0) { sky_color(dx, dy, dz, A, bounces, cr, cg, cb); alive = false; continue; }
             if (bounces == 0) ++n_primary;
             if (a.early_out && best.t == 0.0 && best.C == 0.0) { ++n_early; ++n_black; alive = false; continue; }
-            const Record rec = make_record(a.sc.exact, best, ox, oy, oz, dx, dy, dz);
+            const Record rec = make_record(a.sc, best, ox, oy, oz, dx, dy, dz);
             double rx, ry, rz;
             random_in_hemisphere((uint32_t)q, 0u, blk, a.key0, a.key1, rec.nx, rec.ny, rec.nz, rx, ry, rz);
             const double tgx = dadd(dadd(rec.px, rec.nx), rx);
@@ -562,6 +562,42 @@ __global__ void philox_kernel(const uint32_t* __restrict__ ctr, const uint32_t* 
         const uint4 w = philox4x32_10(ctr[4 * q], ctr[4 * q + 1], ctr[4 * q + 2], ctr[4 * q + 3], key[0], key[1]);
         out[4 * q] = w.x; out[4 * q + 1] = w.y; out[4 * q + 2] = w.z; out[4 * q + 3] = w.w;
     }
+}
+
+// Self-check of ddiv_t() (the short correctly-rounded division of the hit distance) against __ddiv_rn on random
+// operand pairs: exponents of A spread over +-260 and of num over +-760 so that both the short form and the
+// fallback ranges are exercised, plus zeros, denormals, infinities and all-ones / all-zeros mantissas.
+__global__ void div_check_kernel(unsigned long long n, unsigned long long seed, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long z = seed + i * 0x9E3779B97F4A7C15ull, w[3];
+        for (int j = 0; j < 3; ++j) {  // splitmix64
+            z += 0x9E3779B97F4A7C15ull;
+            unsigned long long x = z;
+            x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; w[j] = x ^ (x >> 31);
+        }
+        unsigned long long ma = w[0] & 0xfffffffffffffull, mn = w[1] & 0xfffffffffffffull;
+        const unsigned sel = (unsigned)(w[2] & 15u);
+        if (sel == 1) ma |= 0xffffffffff000ull;      // mantissa near all ones
+        if (sel == 2) ma &= 0x0000000000fffull;      // mantissa near a power of two
+        if (sel == 3) mn |= 0xffffffffff000ull;
+        if (sel == 4) mn &= 0x0000000000fffull;
+        const int ea = (int)((w[2] >> 8) % 521u) - 260, en = (int)((w[2] >> 20) % 1521u) - 760;
+        double A = __longlong_as_double((long long)(((unsigned long long)(ea + 1023) << 52) | ma));
+        double num = __longlong_as_double((long long)(((unsigned long long)(en + 1023) << 52) | mn | ((w[2] >> 40) << 63)));
+        if (sel == 5) num = 0.0;
+        if (sel == 6) num = -0.0;
+        if (sel == 7) num = __longlong_as_double((long long)(mn >> 3));                    // denormal numerator
+        if (sel == 8 && (w[2] >> 41) % 64 == 0) num = __longlong_as_double(0x7ff0000000000000ll);
+        if (sel == 9 && (w[2] >> 41) % 64 == 0) A = __longlong_as_double(0x7ff0000000000000ll);
+        if (sel == 10 && (w[2] >> 41) % 64 == 0) A = 0.0;
+        const RcpA d = make_rcp(A);
+        const double q = ddiv_t(num, d), ref = __ddiv_rn(num, A);
+        const bool same = __double_as_longlong(q) == __double_as_longlong(ref) || (q != q && ref != ref);
+        if (!same) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 // FP32 roofline denominator: 8 independent FFMA chains per thread, register operands only.

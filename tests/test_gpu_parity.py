@@ -50,6 +50,13 @@ def test_write_color_bitwise(rt):
     assert np.array_equal(rt.write_color(sums, 500), ol.write_color_batch("orc", sums, 500))
 
 
+def test_short_division_is_the_ieee_quotient(rt):
+    """t = num / A is formed from one reciprocal per cast plus two exact-residual corrections (rt_device.cuh
+    ddiv_t); it must equal __ddiv_rn bit for bit on every operand class (tolerance: none)."""
+    for seed in (1, 2, 3):
+        assert rt.check_division(200_000_000, seed) == 0
+
+
 # ------------------------------------------------------------------ hittable_list::hit
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", ["ref_hit_book.npz", "ref_hit_book_tmin_tmax.npz", "ref_hit_book_bounce.npz"])
