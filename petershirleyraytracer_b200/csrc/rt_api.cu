@@ -111,11 +111,12 @@ void tile_layout(const rt_params* p, rt_tile_layout* L) {
     L->shard_bytes = (int64_t)L->tiles_per_shard * rt::kTilePix * 4;
 }
 
-// AUTO -> FILTERED while the cull array fits in shared memory (the BVH path takes over above that).
+// AUTO: the BVH traversal wherever a BVH was built.  With the SAH build it is at least as fast as the linear
+// cull scan at every scene size measured on B200 (tools/mode_compare.py: 2 spheres 1005 vs 978 Msamples/s, 40:
+// 612 vs 602, 145: 466 vs 395, 485: 360 vs 194, 1939: 331 vs 42); below 16 spheres, where the two are equal, the
+// scan is kept (one scan step, no tree).
 int resolve_scan_mode(const rt_scene* sc, int mode, int* out) {
-    // AUTO: the linear cull scan while it is cheaper than a traversal, the BVH for large scenes
-    // (measured crossover on B200: ~200 spheres, tools/mode_compare.py)
-    if (mode == RT_SCAN_AUTO) mode = (!sc->cull_ok) ? RT_SCAN_EXACT : (sc->n <= 256 ? RT_SCAN_FILTERED : RT_SCAN_BVH);
+    if (mode == RT_SCAN_AUTO) mode = (!sc->cull_ok) ? RT_SCAN_EXACT : (sc->n < 16 ? RT_SCAN_FILTERED : RT_SCAN_BVH);
     if (mode == RT_SCAN_FILTERED && !sc->cull_ok)
         return fail(RT_ERR_UNSUPPORTED, "scene has non-finite or huge (>1e15) coordinates: use RT_SCAN_EXACT");
     if (mode == RT_SCAN_BVH && !sc->d_bvh_nodes)

@@ -71,8 +71,88 @@ struct Builder {
         return b;
     }
 
+    static double half_area(const Box& b) {
+        const double dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+    static void grow(Box& b, const Box& o) {
+        for (int a = 0; a < 3; ++a) { b.lo[a] = std::min(b.lo[a], o.lo[a]); b.hi[a] = std::max(b.hi[a], o.hi[a]); }
+    }
+    Box sphere_box(int k) const {
+        Box b;
+        const double rad = std::fabs(r[k]);
+        for (int a = 0; a < 3; ++a) { b.lo[a] = c[3 * k + a] - rad; b.hi[a] = c[3 * k + a] + rad; }
+        return b;
+    }
+
+    // Binned surface-area heuristic (16 bins per axis over the centroid bounds): returns the number of spheres
+    // that go left after partitioning order[first, first+count), or 0 if no split beats an object-median split
+    // (all centroids in one bin).  Besides the usual quality gain this isolates outsized spheres near the root:
+    // the r = 1000 ground sphere of the book scenes would otherwise inflate every box on the way down to its
+    // leaf, and every ray would walk that spine.
+    int sah_split(int first, int count) {
+        constexpr int kBins = 16;
+        double clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int i = first; i < first + count; ++i)
+            for (int a = 0; a < 3; ++a) {
+                clo[a] = std::min(clo[a], c[3 * order[i] + a]);
+                chi[a] = std::max(chi[a], c[3 * order[i] + a]);
+            }
+        double best_cost = INFINITY;
+        int best_axis = -1, best_bin = -1;
+        for (int axis = 0; axis < 3; ++axis) {
+            const double ext = chi[axis] - clo[axis];
+            if (!(ext > 0.0) || !std::isfinite(ext)) continue;
+            const double scale = kBins / ext;
+            Box bb[kBins];
+            int bn[kBins];
+            for (int b = 0; b < kBins; ++b) {
+                bn[b] = 0;
+                for (int a = 0; a < 3; ++a) { bb[b].lo[a] = INFINITY; bb[b].hi[a] = -INFINITY; }
+            }
+            for (int i = first; i < first + count; ++i) {
+                const int k = order[i];
+                int b = (int)((c[3 * k + axis] - clo[axis]) * scale);
+                b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+                ++bn[b];
+                grow(bb[b], sphere_box(k));
+            }
+            double right_area[kBins];
+            int right_n[kBins];
+            Box acc;
+            for (int a = 0; a < 3; ++a) { acc.lo[a] = INFINITY; acc.hi[a] = -INFINITY; }
+            int n_acc = 0;
+            for (int b = kBins - 1; b > 0; --b) {
+                if (bn[b]) grow(acc, bb[b]);
+                n_acc += bn[b];
+                right_area[b] = n_acc ? half_area(acc) : 0.0;
+                right_n[b] = n_acc;
+            }
+            for (int a = 0; a < 3; ++a) { acc.lo[a] = INFINITY; acc.hi[a] = -INFINITY; }
+            n_acc = 0;
+            for (int b = 0; b < kBins - 1; ++b) {  // split between bin b and b+1
+                if (bn[b]) grow(acc, bb[b]);
+                n_acc += bn[b];
+                if (n_acc == 0 || right_n[b + 1] == 0) continue;
+                const double cost = half_area(acc) * n_acc + right_area[b + 1] * right_n[b + 1];
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+            }
+        }
+        if (best_axis < 0) return 0;
+        const double ext = chi[best_axis] - clo[best_axis], scale = kBins / ext;
+        const double lo = clo[best_axis];
+        const int axis = best_axis, bin = best_bin;
+        auto mid = std::partition(order.begin() + first, order.begin() + first + count, [&](int32_t k) {
+            int b = (int)((c[3 * k + axis] - lo) * scale);
+            b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+            return b <= bin;
+        });
+        const int left = (int)(mid - (order.begin() + first));
+        return (left > 0 && left < count) ? left : 0;
+    }
+
     // returns the child reference for spheres order[first, first+count)
-    int32_t build(int first, int count) {
+    int32_t build(int first, int count, int depth = 0) {
         if (count <= kBvhLeafMax) {
             const int32_t at = (int32_t)out->leaf_idx.size();
             // inside a leaf keep list order (not required for correctness; keeps tests readable)
@@ -80,23 +160,27 @@ struct Builder {
             for (int i = 0; i < count; ++i) out->leaf_idx.push_back(order[first + i]);
             return (int32_t)(0x80000000u | ((uint32_t)at << 3) | (uint32_t)count);
         }
-        // split at the object median of the centroid axis with the largest extent
-        double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-        for (int i = first; i < first + count; ++i)
-            for (int a = 0; a < 3; ++a) {
-                lo[a] = std::min(lo[a], c[3 * order[i] + a]);
-                hi[a] = std::max(hi[a], c[3 * order[i] + a]);
-            }
-        int axis = 0;
-        for (int a = 1; a < 3; ++a) if (hi[a] - lo[a] > hi[axis] - lo[axis]) axis = a;
-        const int mid = count / 2;
-        std::nth_element(order.begin() + first, order.begin() + first + mid, order.begin() + first + count,
-                         [&](int32_t x, int32_t y) { return c[3 * x + axis] < c[3 * y + axis]; });
+        // below depth 24 only median splits: bounds the tree depth (device traversal stack: 48 entries)
+        int mid = depth < 24 ? sah_split(first, count) : 0;
+        if (mid == 0) {
+            // degenerate centroids (coincident spheres): object median of the axis with the largest extent
+            double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int i = first; i < first + count; ++i)
+                for (int a = 0; a < 3; ++a) {
+                    lo[a] = std::min(lo[a], c[3 * order[i] + a]);
+                    hi[a] = std::max(hi[a], c[3 * order[i] + a]);
+                }
+            int axis = 0;
+            for (int a = 1; a < 3; ++a) if (hi[a] - lo[a] > hi[axis] - lo[axis]) axis = a;
+            mid = count / 2;
+            std::nth_element(order.begin() + first, order.begin() + first + mid, order.begin() + first + count,
+                             [&](int32_t x, int32_t y) { return c[3 * x + axis] < c[3 * y + axis]; });
+        }
         const int32_t me = (int32_t)out->nodes.size();
         out->nodes.push_back(BvhNode{});
         const Box b0 = bounds(first, mid), b1 = bounds(first + mid, count - mid);
-        const int32_t c0 = build(first, mid);
-        const int32_t c1 = build(first + mid, count - mid);
+        const int32_t c0 = build(first, mid, depth + 1);
+        const int32_t c1 = build(first + mid, count - mid, depth + 1);
         BvhNode& n = out->nodes[me];
         store_box(b0, n.lo0, n.hi0);
         store_box(b1, n.lo1, n.hi1);

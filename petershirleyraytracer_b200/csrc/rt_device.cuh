@@ -371,7 +371,7 @@ __device__ __forceinline__ bool exact_test_unordered(const double4* __restrict__
 // here), a subtree is skipped only if it is missed or its entry distance is strictly beyond the current
 // best, and every sphere of a visited leaf runs the FP64 test above.  Requires tmin >= 0 and a finite,
 // non-zero direction (callers route other rays to the sequential scan).  Nearer child first.
-constexpr int kBvhStack = 40;
+constexpr int kBvhStack = 48;
 __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double oy, double oz, double dx, double dy,
                                          double dz, double A, double tmin, double tmax, uint32_t& n_exact,
                                          uint32_t& n_nodes, bool& overflow) {
