@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 1
+#define RT_ABI_VERSION 2
 
 typedef enum {
     RT_OK = 0,
@@ -57,7 +57,7 @@ enum { RT_SCAN_FILTERED = 0, RT_SCAN_EXACT = 1, RT_SCAN_BVH = 2, RT_SCAN_AUTO = 
 /* The constants main() and ray_color hard-code, as parameters. */
 typedef struct {
     int32_t width, height;       /* programs/main.cc:57-58 */
-    int32_t spp;                 /* programs/main.cc:66 */
+    int32_t spp;                 /* programs/main.cc:66; 1 .. 2^20 */
     int32_t max_depth;           /* programs/main.cc:68; depth < 0 ends a path (main.cc:36) -> max_depth+1 casts */
     uint64_t seed;               /* Philox key */
     double tmin;                 /* programs/main.cc:40 passes 0 */
@@ -117,6 +117,20 @@ int rt_render_device(const rt_scene* scene, const rt_camera* cam, const rt_param
                      void* d_radiance_sum, void* stream);
 /* Waits for the last rt_render_device on this scene and reads its counters. */
 int rt_render_finish(const rt_scene* scene, rt_stats* stats_out);
+
+/* Progressive / resumable rendering (replaces the per-scanline progress of programs/main.cc:74 with real
+ * checkpoints).  One pass traces samples [sample_begin, sample_begin + params->spp) of every pixel -- the Philox
+ * streams are keyed on (pixel, absolute sample index) -- and ADDS their colours to the accumulator: W*H*3
+ * uint64, 20.44 fixed point, frame pixel order (row 0 = top), zeroed by the caller before the first pass.  Integer
+ * sums do not depend on order, so ANY split of [0, S) into passes leaves the same accumulator, and the same
+ * frame, bit for bit, as a single render of S spp; the accumulator can be saved and a render resumed later.
+ * rgba (optional) = write_color over all sample_begin + spp samples so far.  sample_begin + spp <= 2^20.
+ * With shard_count > 1 a rank touches only its own tiles of d_accum; d_rgba is then the compact shard buffer. */
+int64_t rt_accum_bytes(const rt_params* params);
+int rt_render_pass(const rt_scene* scene, const rt_camera* cam, const rt_params* params, int32_t sample_begin,
+                   uint64_t* accum /* host, in/out */, uint8_t* rgba_out /* host, may be NULL */, rt_stats* stats_out);
+int rt_render_pass_device(const rt_scene* scene, const rt_camera* cam, const rt_params* params, int32_t sample_begin,
+                          void* d_accum, void* d_rgba /* may be NULL */, void* stream);
 
 int rt_get_tile_layout(const rt_params* params, rt_tile_layout* out);
 /* d_gathered: shard_count consecutive shard buffers (all-gather output) -> d_rgba frame. */

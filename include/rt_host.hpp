@@ -270,6 +270,41 @@ inline frame render(const hittable& world, const camera& cam, int width, int hei
     return render(dw, cam, default_params(width, height, spp, max_depth, seed));
 }
 
+// Progressive / resumable form of the same loop (where the reference can only report "Scanline remaining",
+// programs/main.cc:74): add(n) traces the next n samples of every pixel and folds them into integer sums, so
+// the frame after any sequence of add() calls equals a single render of that many samples bit for bit;
+// sums() / resume() let a caller checkpoint the accumulator and continue later (or on another GPU).
+class progressive_render {
+public:
+    progressive_render(const device_world& world, const camera& cam, const rt_params& p)
+        : world_(world), cam_(to_abi(cam)), p_(p), accum_((size_t)p.width * p.height * 3, 0) {
+        frame_.width = p.width; frame_.height = p.height;
+        frame_.rgba.resize((size_t)p.width * p.height * 4);
+    }
+    const frame& add(int samples) {
+        rt_params q = p_;
+        q.spp = samples;
+        check(rt_render_pass(world_.handle(), &cam_, &q, done_, accum_.data(), frame_.rgba.data(), &frame_.stats));
+        done_ += samples;
+        return frame_;
+    }
+    int samples_done() const { return done_; }
+    const frame& current() const { return frame_; }
+    const std::vector<uint64_t>& sums() const { return accum_; }  // 20.44 fixed point, W*H*3, row 0 = top
+    void resume(const std::vector<uint64_t>& sums, int samples_done) {
+        if (sums.size() != accum_.size() || samples_done < 0) throw error(RT_ERR_INVALID, "checkpoint does not match this frame");
+        accum_ = sums; done_ = samples_done;
+    }
+
+private:
+    const device_world& world_;
+    rt_camera cam_;
+    rt_params p_;
+    std::vector<uint64_t> accum_;
+    frame frame_;
+    int done_ = 0;
+};
+
 // programs/main.cc:70 + the per-pixel lines write_color emits (programs/color.h:21-23), from the 8-bit frame.
 inline void write_ppm(std::ostream& out, const frame& f) {
     std::string s = "P3\n" + std::to_string(f.width) + ' ' + std::to_string(f.height) + "\n255\n";

@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "rt_abi_version", "rt_last_error", "rt_upload_scene", "rt_free_scene", "rt_scene_size", "rt_render",
     "rt_render_device", "rt_render_finish", "rt_get_tile_layout", "rt_deinterleave", "rt_primary_hits", "rt_hit",
     "rt_ray_color", "rt_write_color", "rt_get_ray", "rt_philox", "rt_measure_fp32_peak", "rt_device_info",
-    "rt_check_division",
+    "rt_check_division", "rt_accum_bytes", "rt_render_pass", "rt_render_pass_device",
 ]
 
 
@@ -90,6 +90,12 @@ def lib() -> C.CDLL:
     L.rt_philox.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int32, C.c_int32, C.POINTER(C.c_uint32)]
     L.rt_measure_fp32_peak.argtypes = [C.c_int32, dp, dp]
     L.rt_device_info.argtypes = [C.c_int32, ip, ip, ip, C.c_char_p, C.c_int32]
+    L.rt_accum_bytes.restype = C.c_int64
+    L.rt_accum_bytes.argtypes = [C.POINTER(RtParams)]
+    L.rt_render_pass.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtParams), C.c_int32, C.POINTER(C.c_uint64),
+                                 C.POINTER(C.c_uint8), C.POINTER(RtStats)]
+    L.rt_render_pass_device.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtParams), C.c_int32, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
     L.rt_check_division.argtypes = [C.c_int32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
     _lib = L
     return L
@@ -221,6 +227,31 @@ def render(scene: Scene, cam: Camera, params: RtParams, want_sums: bool = False)
     _check(lib().rt_render(scene.handle, C.byref(cs), C.byref(params), rgba.ctypes.data_as(C.POINTER(C.c_uint8)),
                            _dptr(sums) if want_sums else None, C.byref(st)))
     return rgba, sums, st.as_dict()
+
+
+def render_pass(scene: Scene, cam: Camera, params: RtParams, sample_begin: int, accum: np.ndarray | None = None,
+                want_rgba: bool = True):
+    """rt_render_pass: trace samples [sample_begin, sample_begin + params.spp) and add them to `accum` (H x W x 3
+    uint64 fixed-point sums; None = start from zero).  Returns (accum, rgba over all samples so far, stats)."""
+    W, H = params.width, params.height
+    if accum is None:
+        accum = np.zeros((H, W, 3), dtype=np.uint64)
+    if accum.shape != (H, W, 3) or accum.dtype != np.uint64 or not accum.flags.c_contiguous:
+        raise ValueError("accum must be a C-contiguous (H, W, 3) uint64 array")
+    rgba = np.empty((H, W, 4), dtype=np.uint8) if want_rgba else None
+    st = RtStats()
+    cs = cam.c_struct()
+    _check(lib().rt_render_pass(scene.handle, C.byref(cs), C.byref(params), sample_begin,
+                                accum.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                rgba.ctypes.data_as(C.POINTER(C.c_uint8)) if want_rgba else None, C.byref(st)))
+    return accum, rgba, st.as_dict()
+
+
+def render_pass_device(scene: Scene, cam: Camera, params: RtParams, sample_begin: int, d_accum: int, d_rgba: int = 0,
+                       stream: int = 0) -> None:
+    cs = cam.c_struct()
+    _check(lib().rt_render_pass_device(scene.handle, C.byref(cs), C.byref(params), sample_begin, C.c_void_p(d_accum),
+                                       C.c_void_p(d_rgba) if d_rgba else None, C.c_void_p(stream) if stream else None))
 
 
 def render_device(scene: Scene, cam: Camera, params: RtParams, d_rgba: int, d_sums: int = 0, stream: int = 0) -> None:

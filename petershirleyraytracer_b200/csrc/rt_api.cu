@@ -94,7 +94,7 @@ int check_params(const rt_params* p) {
     if (!p) return fail(RT_ERR_INVALID, "params is NULL");
     if (p->width < 2 || p->height < 2) return fail(RT_ERR_INVALID, "width and height must be >= 2 (u,v divide by W-1, H-1)");
     if ((int64_t)p->width * p->height > (int64_t)1 << 30) return fail(RT_ERR_INVALID, "frame too large");
-    if (p->spp < 1 || p->spp > (1 << 24)) return fail(RT_ERR_INVALID, "spp must be in [1, 2^24]");
+    if (p->spp < 1 || p->spp > (1 << 20)) return fail(RT_ERR_INVALID, "spp must be in [1, 2^20] (radiance sums are 20.44 fixed point)");
     if (p->max_depth > 1000) return fail(RT_ERR_INVALID, "max_depth must be <= 1000");
     if (p->shard_count < 1 || p->shard_rank < 0 || p->shard_rank >= p->shard_count)
         return fail(RT_ERR_INVALID, "bad shard_rank / shard_count");
@@ -145,7 +145,7 @@ int grow(void** p, size_t* cap, size_t need) {
 }
 
 int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* d_rgba, void* d_sum,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, int sample_base = 0, void* d_frame_accum = nullptr) {
     int mode = 0;
     int rc = resolve_scan_mode(sc, p->scan_mode, &mode);
     if (rc) return rc;
@@ -169,6 +169,7 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     a.compact_out = p->shard_count > 1;
     a.out = (uchar4*)d_rgba; a.sum_out = (double*)d_sum;
     a.unit_counter = sc->d_tile_counter; a.stats = sc->d_stats;
+    a.sample_base = sample_base; a.frame_accum = (unsigned long long*)d_frame_accum;
 
     int R = p->reserved[0];
     if (R == 0) R = 2;
@@ -222,7 +223,7 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     }
     RT_CUDA(cudaMemsetAsync(sc->d_tile_counter, 0, sizeof(unsigned int), stream));
     RT_CUDA(cudaMemsetAsync(sc->d_stats, 0, rt::kNumStats * sizeof(unsigned long long), stream));
-    if (a.compact_out) RT_CUDA(cudaMemsetAsync(d_rgba, 0, (size_t)L.shard_bytes, stream));
+    if (a.compact_out && d_rgba) RT_CUDA(cudaMemsetAsync(d_rgba, 0, (size_t)L.shard_bytes, stream));
     RT_CUDA(cudaEventRecord(sc->ev0, stream));
     kern<<<grid, rt::kThreads, S.total, stream>>>(a);
     RT_CUDA(cudaGetLastError());
@@ -382,6 +383,49 @@ int rt_render_device(const rt_scene* scene, const rt_camera* cam, const rt_param
     if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->ev1));
     if (d_sum && p->shard_count > 1) return fail(RT_ERR_INVALID, "radiance sums are only available for shard_count == 1");
     return launch_render(sc, cam, p, d_rgba, d_sum, (cudaStream_t)stream);
+}
+
+int64_t rt_accum_bytes(const rt_params* p) {
+    if (check_params(p)) return RT_ERR_INVALID;
+    return (int64_t)p->width * p->height * 3 * (int64_t)sizeof(unsigned long long);
+}
+
+int rt_render_pass_device(const rt_scene* scene, const rt_camera* cam, const rt_params* p, int32_t sample_begin,
+                          void* d_accum, void* d_rgba, void* stream) {
+    if (!scene || !cam || !d_accum) return fail(RT_ERR_INVALID, "NULL argument");
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (sample_begin < 0 || (int64_t)sample_begin + p->spp > (1 << 20))
+        return fail(RT_ERR_INVALID, "sample_begin + spp must stay within [0, 2^20] (radiance sums are 20.44 fixed point)");
+    rt_scene* sc = const_cast<rt_scene*>(scene);
+    DeviceGuard guard(sc->device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->ev1));
+    return launch_render(sc, cam, p, d_rgba, nullptr, (cudaStream_t)stream, sample_begin, d_accum);
+}
+
+int rt_render_pass(const rt_scene* scene, const rt_camera* cam, const rt_params* p, int32_t sample_begin,
+                   uint64_t* accum, uint8_t* rgba_out, rt_stats* st) {
+    if (!scene || !cam || !accum) return fail(RT_ERR_INVALID, "NULL argument");
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (p->shard_count != 1) return fail(RT_ERR_INVALID, "rt_render_pass renders whole frames; use rt_render_pass_device for shards");
+    rt_scene* sc = const_cast<rt_scene*>(scene);
+    DeviceGuard guard(sc->device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    const size_t npix = (size_t)p->width * p->height;
+    DevBuf<unsigned long long> d_acc;
+    RT_CUDA(d_acc.alloc(npix * 3));
+    RT_CUDA(cudaMemcpy(d_acc.p, accum, npix * 3 * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    rc = grow(&sc->d_frame, &sc->frame_cap, npix * 4);
+    if (rc) return rc;
+    rc = rt_render_pass_device(scene, cam, p, sample_begin, d_acc.p, sc->d_frame, nullptr);
+    if (rc) return rc;
+    rc = finish_render(sc, st);
+    if (rc) return rc;
+    RT_CUDA(cudaMemcpy(accum, d_acc.p, npix * 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (rgba_out) RT_CUDA(cudaMemcpy(rgba_out, sc->d_frame, npix * 4, cudaMemcpyDeviceToHost));
+    return RT_OK;
 }
 
 int rt_render_finish(const rt_scene* scene, rt_stats* st) {

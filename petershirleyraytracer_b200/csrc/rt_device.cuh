@@ -118,6 +118,8 @@ struct RenderArgs {
     int compact_out;
     uchar4* out;
     double* sum_out;               // optional W*H*3
+    unsigned long long* frame_accum;  // optional W*H*3 fixed-point sums carried across passes (progressive rendering)
+    int sample_base;               // first sample index of this pass (Philox streams are keyed on the absolute index)
     unsigned int* unit_counter;    // persistent-warp work queue head
     unsigned long long* accum;     // tiles_local * 192 fixed-point sums (used when chunks > 1)
     unsigned int* tile_done;       // tiles_local chunk-completion counters

@@ -76,7 +76,7 @@ __device__ __forceinline__ int unit_spp(const RenderArgs& a, int chunk) {
 template <bool kFromGlobal>
 __device__ __forceinline__ void finalize_tile(const RenderArgs& a, int tile_l, const unsigned long long* src, int lane) {
     const TileGeom g = tile_geom(a, tile_l);
-    const double one_over_samples = ddiv(1.0, (double)a.spp);  // programs/color.h:16
+    const double one_over_samples = ddiv(1.0, (double)(a.sample_base + a.spp));  // programs/color.h:16 (all samples so far)
     const double inv_fs = 1.0 / (double)(1ull << kFixShift);
 #pragma unroll 1
     for (int pj = 0; pj < kTilePix / 32; ++pj) {  // uniform trip count (lane-strided bounds would mark the warp divergent)
@@ -86,15 +86,22 @@ __device__ __forceinline__ void finalize_tile(const RenderArgs& a, int tile_l, c
         unsigned long long v0, v1, v2;
         if (kFromGlobal) { v0 = __ldcg(src + p * 3); v1 = __ldcg(src + p * 3 + 1); v2 = __ldcg(src + p * 3 + 2); }
         else { v0 = src[p * 3]; v1 = src[p * 3 + 1]; v2 = src[p * 3 + 2]; }
+        const size_t frame_idx = (size_t)(g.y0 + ly) * a.W + (g.x0 + lx);
+        if (a.frame_accum) {  // progressive pass: integer sums continue from the earlier passes (order-independent)
+            unsigned long long* fa = a.frame_accum + frame_idx * 3;
+            v0 += fa[0]; v1 += fa[1]; v2 += fa[2];
+            fa[0] = v0; fa[1] = v1; fa[2] = v2;
+        }
         const double sr = __ull2double_rn(v0) * inv_fs, sg = __ull2double_rn(v1) * inv_fs, sb = __ull2double_rn(v2) * inv_fs;
         uchar4 q;
         q.x = (unsigned char)write_color_channel(sr, one_over_samples);
         q.y = (unsigned char)write_color_channel(sg, one_over_samples);
         q.z = (unsigned char)write_color_channel(sb, one_over_samples);
         q.w = 255;
-        const size_t frame_idx = (size_t)(g.y0 + ly) * a.W + (g.x0 + lx);
-        if (a.compact_out) a.out[(size_t)tile_l * kTilePix + p] = q;
-        else a.out[frame_idx] = q;
+        if (a.out) {
+            if (a.compact_out) a.out[(size_t)tile_l * kTilePix + p] = q;
+            else a.out[frame_idx] = q;
+        }
         if (a.sum_out) {
             a.sum_out[frame_idx * 3 + 0] = sr; a.sum_out[frame_idx * 3 + 1] = sg; a.sum_out[frame_idx * 3 + 2] = sb;
         }
@@ -279,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R>::kMinBlocks) render_
                     const uint32_t id = c.next + rank;
                     const uint32_t ns = (uint32_t)unit_spp(a, c.chunk);
                     const uint32_t p = id / ns;
-                    const uint32_t s = (uint32_t)(c.chunk * a.chunk_spp) + (id - p * ns);
+                    const uint32_t s = (uint32_t)(a.sample_base + c.chunk * a.chunk_spp) + (id - p * ns);
                     const int ly = (int)p / g.tw, lx = (int)p - ly * g.tw;
                     const int i = g.x0 + lx, j = a.H - 1 - (g.y0 + ly);  // j from the bottom (programs/main.cc:72)
                     const uint32_t pixid = (uint32_t)(j * a.W + i);

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(rt):
     L = rt.lib()
     for name in _header_functions():
         assert hasattr(L, name), name
-    assert L.rt_abi_version() == 1
+    assert L.rt_abi_version() == 2
 
 
 def test_struct_layouts(rt):

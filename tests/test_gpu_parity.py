@@ -316,6 +316,9 @@ def test_host_main_prints_the_oracle_frame_as_p3(rt, default_scene):
     c, r = default_scene
     orgb, _, _ = ol.render("orc", c, r, rt.Camera.default().as12(), W, H, spp, depth, seed=seed, rng_mode=ol.RNG_PHILOX)
     assert np.array_equal(px, orgb)
+    # rt::progressive_render (three passes) prints the same text and reports its progress on stderr
+    prog = subprocess.run([exe, str(W), str(spp), str(depth), str(seed), "3"], capture_output=True, check=True)
+    assert prog.stdout.decode() == out and b"Samples done: 8" in prog.stderr
 
 
 def test_dist_module_single_rank(rt, book):
@@ -381,6 +384,46 @@ def test_bvh_ties_and_tiny_scenes(rt):
             assert np.array_equal(idx, oi)
 
 
+def _adversarial_scene(kind, rng):
+    if kind == "coincident":        # every centre identical: no SAH split exists -> median fallback, ties by list order
+        c = np.tile([[1.0, 2.0, -3.0]], (300, 1))
+        r = rng.choice([0.5, 0.5, 0.75, 1.0], size=300)
+    elif kind == "nested":          # concentric shells + a cloud inside: outsized boxes at every level
+        c = np.concatenate([np.zeros((40, 3)), rng.normal(size=(400, 3)) * 0.3])
+        r = np.concatenate([np.geomspace(0.01, 1e4, 40), np.full(400, 0.02)])
+    elif kind == "line":            # collinear centres with geometrically growing radii (deep one-sided SAH splits)
+        x = np.geomspace(1e-3, 1e5, 600)
+        c = np.stack([x, np.zeros_like(x), np.zeros_like(x)], axis=1)
+        r = 0.3 * x
+    else:                           # clusters with log-uniform radii, duplicates and a giant
+        cen = rng.normal(size=(12, 3)) * 20
+        c = cen[rng.integers(0, 12, size=3000)] + rng.normal(size=(3000, 3))
+        r = np.exp(rng.uniform(np.log(1e-3), np.log(3.0), size=3000))
+        c[100:120] = c[100]; r[100:120] = r[100]
+        c = np.concatenate([c, [[0.0, -5000.0, 0.0]]]); r = np.concatenate([r, [4990.0]])
+    return np.ascontiguousarray(c, dtype=np.float64), np.ascontiguousarray(r, dtype=np.float64)
+
+
+@pytest.mark.parametrize("kind", ["coincident", "nested", "line", "clusters"])
+def test_bvh_sah_build_on_adversarial_scenes(rt, kind):
+    """The SAH builder's corner cases (no valid split, outsized spheres at every level, one-sided splits down
+    to the depth limit) must not change the answer: hit records equal the reference's list scan bit for bit."""
+    rng = np.random.default_rng(len(kind))
+    c, r = _adversarial_scene(kind, rng)
+    n = 6000
+    k = rng.integers(0, len(r), size=n)
+    u = rng.normal(size=(n, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    org = c[k] + rng.choice([0.0, 1.0, 1.0, 3.0], size=(n, 1)) * r[k][:, None] * u
+    d = rng.normal(size=(n, 3))
+    with rt.Scene(c, r) as sc:
+        idx, rec = rt.hit(sc, org, d, scan_mode=2)
+        assert sc is not None
+    oi, orec = ol.hit_batch("orc", c, r, org, d)
+    assert np.array_equal(idx, oi) and np.array_equal(bits(rec), bits(orec))
+    assert (oi >= 0).mean() > 0.3
+
+
 def test_bvh_render_equals_linear_scan(rt, book):
     from petershirleyraytracer_b200 import scenes
     c, r = book
@@ -437,6 +480,32 @@ def test_two_scenes_on_two_streams_do_not_clobber_the_constant_bank(rt, book, de
             torch.cuda.synchronize()
             assert np.array_equal(f1.cpu().numpy().reshape(H, W, 4), ref1)
             assert np.array_equal(f2.cpu().numpy().reshape(H, W, 4), ref2)
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_progressive_passes_equal_one_render(rt, book, mode):
+    """any split of the sample range into passes leaves the same accumulator and frame as a single
+    render (integer sums, Philox keyed on the absolute sample index); a saved accumulator resumes the render."""
+    from petershirleyraytracer_b200 import scenes
+    c, r = book
+    W, H, spp = 72, 40, 12
+    cam = scenes.book_camera(W, H)
+    with rt.Scene(c, r) as sc:
+        full, sums, st = rt.render(sc, cam, rt.make_params(W, H, spp, 50, seed=5, scan_mode=mode, early_out=False), want_sums=True)
+        one_acc, one_rgba, _ = rt.render_pass(sc, cam, rt.make_params(W, H, spp, 50, seed=5, scan_mode=mode, early_out=False), 0)
+        acc, casts = None, 0
+        for begin, n in ((0, 5), (5, 1), (6, 6)):
+            acc, rgba, pst = rt.render_pass(sc, cam, rt.make_params(W, H, n, 50, seed=5, scan_mode=mode, early_out=False), begin, acc)
+            casts += pst["casts"]
+        saved = acc.copy()                      # "checkpoint": continue from the saved sums with 4 more samples
+        acc2, rgba2, _ = rt.render_pass(sc, cam, rt.make_params(W, H, 4, 50, seed=5, scan_mode=mode, early_out=False), spp, saved)
+        full16, _, _ = rt.render(sc, cam, rt.make_params(W, H, spp + 4, 50, seed=5, scan_mode=mode, early_out=False))
+        with pytest.raises(rt.RtError):
+            rt.render_pass(sc, cam, rt.make_params(W, H, 8, 50), (1 << 20) - 4)
+    assert np.array_equal(one_rgba, full) and np.array_equal(rgba, full) and np.array_equal(acc, one_acc)
+    assert casts == st["casts"]
+    assert np.array_equal(acc.astype(np.float64) / 2.0**44, sums)       # the sums write_color receives
+    assert np.array_equal(rgba2, full16)
 
 
 def test_tmin_parameter_and_no_jitter(rt, book):
