@@ -99,6 +99,10 @@ const char* rt_last_error(void);
  * (programs/sphere.h:18-19): centres_xyz = 3n doubles, radii = n doubles, list order.  Uploads to
  * `device`; builds the FP32 cull array, the FP64 exact array and the flattened BVH. */
 int rt_upload_scene(const double* centres_xyz, const double* radii, int32_t n, int32_t device, rt_scene** out);
+/* Moved / resized spheres, same count and list order (an animation step).  Device buffers are reused.
+ * refit = 1 keeps the BVH topology and recomputes its boxes (O(n), exact for any motion, cheaper traversal only
+ * while the motion is moderate); refit = 0 rebuilds the tree.  Waits for renders in flight on this scene. */
+int rt_update_scene(rt_scene* scene, const double* centres_xyz, const double* radii, int32_t n, int32_t refit);
 void rt_free_scene(rt_scene* scene);
 int rt_scene_size(const rt_scene* scene);
 

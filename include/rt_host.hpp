@@ -236,6 +236,13 @@ public:
     device_world& operator=(const device_world&) = delete;
     const rt_scene* handle() const { return scene_; }
     int size() const { return rt_scene_size(scene_); }
+    // The same world after its spheres moved or were resized (same objects, same order): re-flattens and
+    // updates the device buffers in place; refit keeps the BVH topology and only recomputes its boxes.
+    void update(const hittable& world, bool refit = true) {
+        std::vector<double> c, r;
+        flatten(world, c, r);
+        check(rt_update_scene(scene_, c.data(), r.data(), (int32_t)r.size(), refit ? 1 : 0));
+    }
 
 private:
     rt_scene* scene_ = nullptr;

@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "rt_abi_version", "rt_last_error", "rt_upload_scene", "rt_free_scene", "rt_scene_size", "rt_render",
     "rt_render_device", "rt_render_finish", "rt_get_tile_layout", "rt_deinterleave", "rt_primary_hits", "rt_hit",
     "rt_ray_color", "rt_write_color", "rt_get_ray", "rt_philox", "rt_measure_fp32_peak", "rt_device_info",
-    "rt_check_division", "rt_accum_bytes", "rt_render_pass", "rt_render_pass_device",
+    "rt_check_division", "rt_update_scene", "rt_accum_bytes", "rt_render_pass", "rt_render_pass_device",
 ]
 
 
@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
     L.rt_philox.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int32, C.c_int32, C.POINTER(C.c_uint32)]
     L.rt_measure_fp32_peak.argtypes = [C.c_int32, dp, dp]
     L.rt_device_info.argtypes = [C.c_int32, ip, ip, ip, C.c_char_p, C.c_int32]
+    L.rt_update_scene.argtypes = [C.c_void_p, dp, dp, C.c_int32, C.c_int32]
     L.rt_accum_bytes.restype = C.c_int64
     L.rt_accum_bytes.argtypes = [C.POINTER(RtParams)]
     L.rt_render_pass.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtParams), C.c_int32, C.POINTER(C.c_uint64),
@@ -198,6 +199,14 @@ class Scene:
 
     def __len__(self) -> int:
         return len(self.radii)
+
+    def update(self, centres, radii, refit: bool = True) -> None:
+        """rt_update_scene: same spheres, moved / resized.  refit keeps the BVH topology (boxes recomputed)."""
+        c, r = _f64(centres).reshape(-1, 3), _f64(radii).reshape(-1)
+        if len(c) != len(self.radii) or len(r) != len(self.radii):
+            raise ValueError("update keeps the sphere count")
+        _check(lib().rt_update_scene(self.handle, _dptr(c), _dptr(r), len(r), int(refit)))
+        self.centres, self.radii = c, r
 
     def close(self) -> None:
         if self._h:

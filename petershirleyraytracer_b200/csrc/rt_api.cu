@@ -60,6 +60,7 @@ struct rt_scene {
     float4* d_bvh_nodes = nullptr;    // flattened BVH (rt_bvh.h), built at upload
     int32_t* d_bvh_leaf = nullptr;
     int bvh_nodes = 0;
+    rt::BvhHost bvh_host;             // topology kept for rt_update_scene's refit
     unsigned int* d_tile_counter = nullptr;   // work-queue head of the persistent warps
     unsigned long long* d_stats = nullptr;
     void* d_accum = nullptr; size_t accum_cap = 0;   // fixed-point radiance per tile pixel (+ chunk counters behind it)
@@ -265,6 +266,65 @@ int batch_grid(const rt_scene* sc, int nrays) {
     return g < 1 ? 1 : (g > cap ? cap : g);
 }
 
+// Builds the scene's arrays from (centres, radii) and copies them into the already allocated device buffers:
+// FP32 cull entries, FP64 exact array, 1/r table, and the flattened BVH (rebuilt, or refitted on the kept
+// topology).  Shared by rt_upload_scene and rt_update_scene.
+int fill_scene(rt_scene* sc, const double* centres_xyz, const double* radii, bool refit) {
+    const int n = sc->n;
+    // FP32 cull entries {c, |c|^2 - r^2 - E_k}: computed in FP64, constant term rounded DOWN.
+    std::vector<float4> filt((size_t)sc->npad + rt::kScanPad);
+    std::vector<double4> exact((size_t)n > 0 ? n : 1);
+    std::vector<double> inv_r((size_t)n > 0 ? n : 1);
+    sc->cull_ok = true;
+    for (int k = 0; k < sc->npad + rt::kScanPad; ++k) {
+        float4 f;
+        if (k < n) {
+            const double cx = centres_xyz[3 * k], cy = centres_xyz[3 * k + 1], cz = centres_xyz[3 * k + 2], r = radii[k];
+            const double a2 = cx * cx + cy * cy + cz * cz, r2 = r * r;
+            const double Ek = rt::kCullEps * (rt::kCullKc * a2 + rt::kCullKr * r2);
+            f.x = (float)cx; f.y = (float)cy; f.z = (float)cz;
+            f.w = round_down_f32(a2 - r2 - Ek);
+            if (!(a2 < rt::kCullMaxMag2) || !(r2 < rt::kCullMaxMag2)) sc->cull_ok = false;  // also catches NaN / inf
+            exact[k] = make_double4(cx, cy, cz, r);
+            inv_r[k] = 1.0 / r;  // IEEE double division on the host == __ddiv_rn(1.0, r)
+        } else {
+            f.x = f.y = f.z = 0.f;
+            f.w = INFINITY;  // q = +inf -> D = -inf: never passes
+        }
+        filt[k] = f;
+    }
+    if (cudaMemcpy(sc->d_filt, filt.data(), filt.size() * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(sc->d_exact, exact.data(), exact.size() * sizeof(double4), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(sc->d_inv_r, inv_r.data(), inv_r.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+        return RT_ERR_CUDA;
+    // flattened BVH (exact closest-hit semantics, rt_bvh.h); finite scenes only
+    if (!sc->cull_ok) {
+        cudaFree(sc->d_bvh_nodes); cudaFree(sc->d_bvh_leaf);
+        sc->d_bvh_nodes = nullptr; sc->d_bvh_leaf = nullptr; sc->bvh_nodes = 0;
+        sc->bvh_host = rt::BvhHost();
+        return RT_OK;
+    }
+    const bool have_tree = sc->d_bvh_nodes && !sc->bvh_host.nodes.empty();
+    if (refit && have_tree) {
+        rt::refit_bvh(centres_xyz, radii, &sc->bvh_host);
+    } else {
+        rt::build_bvh(centres_xyz, radii, n, &sc->bvh_host);
+    }
+    const rt::BvhHost& bvh = sc->bvh_host;
+    const size_t nb = bvh.nodes.size() * sizeof(rt::BvhNode), lb = (bvh.leaf_idx.size() + 1) * sizeof(int32_t);
+    if (!have_tree || (int)bvh.nodes.size() != sc->bvh_nodes) {  // (a rebuild may change the node count)
+        cudaFree(sc->d_bvh_nodes); cudaFree(sc->d_bvh_leaf);
+        sc->d_bvh_nodes = nullptr; sc->d_bvh_leaf = nullptr;
+        if (cudaMalloc(&sc->d_bvh_nodes, nb) != cudaSuccess || cudaMalloc(&sc->d_bvh_leaf, lb) != cudaSuccess) return RT_ERR_CUDA;
+    }
+    sc->bvh_nodes = (int)bvh.nodes.size();
+    if (cudaMemcpy(sc->d_bvh_nodes, bvh.nodes.data(), nb, cudaMemcpyHostToDevice) != cudaSuccess) return RT_ERR_CUDA;
+    if (!bvh.leaf_idx.empty() &&
+        cudaMemcpy(sc->d_bvh_leaf, bvh.leaf_idx.data(), bvh.leaf_idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess)
+        return RT_ERR_CUDA;
+    return RT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -297,49 +357,16 @@ int rt_upload_scene(const double* centres_xyz, const double* radii, int32_t n, i
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete sc; return fail(RT_ERR_CUDA, "cudaGetDeviceProperties failed"); }
     sc->sm_count = prop.multiProcessorCount;
 
-    // FP32 cull entries {c, |c|^2 - r^2 - E_k}: computed in FP64, constant term rounded DOWN.
-    std::vector<float4> filt((size_t)sc->npad + rt::kScanPad);
-    std::vector<double4> exact((size_t)n > 0 ? n : 1);
-    std::vector<double> inv_r((size_t)n > 0 ? n : 1);
-    for (int k = 0; k < sc->npad + rt::kScanPad; ++k) {
-        float4 f;
-        if (k < n) {
-            const double cx = centres_xyz[3 * k], cy = centres_xyz[3 * k + 1], cz = centres_xyz[3 * k + 2], r = radii[k];
-            const double a2 = cx * cx + cy * cy + cz * cz, r2 = r * r;
-            const double Ek = rt::kCullEps * (rt::kCullKc * a2 + rt::kCullKr * r2);
-            f.x = (float)cx; f.y = (float)cy; f.z = (float)cz;
-            f.w = round_down_f32(a2 - r2 - Ek);
-            if (!(a2 < rt::kCullMaxMag2) || !(r2 < rt::kCullMaxMag2)) sc->cull_ok = false;  // also catches NaN / inf
-            exact[k] = make_double4(cx, cy, cz, r);
-            inv_r[k] = 1.0 / r;  // IEEE double division on the host == __ddiv_rn(1.0, r)
-        } else {
-            f.x = f.y = f.z = 0.f;
-            f.w = INFINITY;  // q = +inf -> D = -inf: never passes
-        }
-        filt[k] = f;
-    }
     int rc = RT_OK;
     do {
-        if (cudaMalloc(&sc->d_filt, filt.size() * sizeof(float4)) != cudaSuccess ||
-            cudaMalloc(&sc->d_exact, exact.size() * sizeof(double4)) != cudaSuccess ||
-            cudaMalloc(&sc->d_inv_r, inv_r.size() * sizeof(double)) != cudaSuccess ||
+        const size_t nf = (size_t)sc->npad + rt::kScanPad, ne = (size_t)(n > 0 ? n : 1);
+        if (cudaMalloc(&sc->d_filt, nf * sizeof(float4)) != cudaSuccess ||
+            cudaMalloc(&sc->d_exact, ne * sizeof(double4)) != cudaSuccess ||
+            cudaMalloc(&sc->d_inv_r, ne * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&sc->d_tile_counter, sizeof(unsigned int)) != cudaSuccess ||
             cudaMalloc(&sc->d_stats, rt::kNumStats * sizeof(unsigned long long)) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
-        if (cudaMemcpy(sc->d_filt, filt.data(), filt.size() * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess ||
-            cudaMemcpy(sc->d_exact, exact.data(), exact.size() * sizeof(double4), cudaMemcpyHostToDevice) != cudaSuccess ||
-            cudaMemcpy(sc->d_inv_r, inv_r.data(), inv_r.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
         if (cudaEventCreate(&sc->ev0) != cudaSuccess || cudaEventCreate(&sc->ev1) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
-        // flattened BVH (exact closest-hit semantics, rt_bvh.h); finite scenes only
-        if (sc->cull_ok) {
-            rt::BvhHost bvh;
-            rt::build_bvh(centres_xyz, radii, n, &bvh);
-            sc->bvh_nodes = (int)bvh.nodes.size();
-            const size_t nb = bvh.nodes.size() * sizeof(rt::BvhNode), lb = (bvh.leaf_idx.size() + 1) * sizeof(int32_t);
-            if (cudaMalloc(&sc->d_bvh_nodes, nb) != cudaSuccess || cudaMalloc(&sc->d_bvh_leaf, lb) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
-            if (cudaMemcpy(sc->d_bvh_nodes, bvh.nodes.data(), nb, cudaMemcpyHostToDevice) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
-            if (!bvh.leaf_idx.empty() &&
-                cudaMemcpy(sc->d_bvh_leaf, bvh.leaf_idx.data(), bvh.leaf_idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
-        }
+        rc = fill_scene(sc, centres_xyz, radii, /*refit=*/false);
     } while (0);
     if (rc != RT_OK) {
         const std::string msg = std::string("scene upload: ") + cudaGetErrorString(cudaGetLastError());
@@ -347,6 +374,22 @@ int rt_upload_scene(const double* centres_xyz, const double* radii, int32_t n, i
         return fail(rc, msg);
     }
     *out = sc;
+    return RT_OK;
+}
+
+int rt_update_scene(rt_scene* sc, const double* centres_xyz, const double* radii, int32_t n, int32_t refit) {
+    if (!sc || (n > 0 && (!centres_xyz || !radii))) return fail(RT_ERR_INVALID, "NULL argument");
+    if (n != sc->n) return fail(RT_ERR_INVALID, "rt_update_scene keeps the sphere count; upload a new scene to change it");
+    DeviceGuard guard(sc->device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    if (sc->pending) { RT_CUDA(cudaEventSynchronize(sc->ev1)); sc->pending = false; }
+    {   // a constant-bank render of the old cull array may still be queued on another stream of this device
+        std::lock_guard<std::mutex> lock(g_const_bank.mu);
+        cudaEvent_t prev = g_const_bank.last[sc->device & 63];
+        if (prev) RT_CUDA(cudaEventSynchronize(prev));
+    }
+    const int rc = fill_scene(sc, centres_xyz, radii, refit != 0);
+    if (rc != RT_OK) return fail(rc, std::string("scene update: ") + cudaGetErrorString(cudaGetLastError()));
     return RT_OK;
 }
 

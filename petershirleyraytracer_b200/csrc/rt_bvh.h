@@ -191,6 +191,40 @@ struct Builder {
 
 }  // namespace bvh_detail
 
+// Refit: same topology (nodes, leaf lists), boxes recomputed for moved / resized spheres.  Children are
+// stored after their parent, so one pass from the last node to the root sees every child box before it is needed.
+// Exactness never depends on the tree's quality, only the traversal cost does; rebuild after large motion.
+inline void refit_bvh(const double* centres, const double* radii, BvhHost* bvh) {
+    using namespace bvh_detail;
+    const int nn = (int)bvh->nodes.size();
+    std::vector<Box> whole((size_t)nn);  // union of both child boxes of node i
+    auto child_box = [&](int32_t ref) {
+        Box b;
+        for (int a = 0; a < 3; ++a) { b.lo[a] = INFINITY; b.hi[a] = -INFINITY; }
+        if (ref >= 0) return whole[(size_t)ref];
+        const int first = (int)(((uint32_t)ref & 0x7fffffffu) >> 3), count = ref & 7;
+        for (int i = 0; i < count; ++i) {
+            const int k = bvh->leaf_idx[(size_t)first + i];
+            const double rad = std::fabs(radii[k]);
+            for (int a = 0; a < 3; ++a) {
+                b.lo[a] = std::min(b.lo[a], centres[3 * k + a] - rad);
+                b.hi[a] = std::max(b.hi[a], centres[3 * k + a] + rad);
+            }
+        }
+        return b;
+    };
+    for (int i = nn - 1; i >= 0; --i) {
+        BvhNode& n = bvh->nodes[(size_t)i];
+        const Box b0 = child_box(n.child0), b1 = child_box(n.child1);
+        const bool e0 = n.child0 < 0 && (n.child0 & 7) == 0, e1 = n.child1 < 0 && (n.child1 & 7) == 0;
+        if (e0) empty_box(n.lo0, n.hi0); else store_box(b0, n.lo0, n.hi0);
+        if (e1) empty_box(n.lo1, n.hi1); else store_box(b1, n.lo1, n.hi1);
+        Box w = b0;
+        for (int a = 0; a < 3; ++a) { w.lo[a] = std::min(w.lo[a], b1.lo[a]); w.hi[a] = std::max(w.hi[a], b1.hi[a]); }
+        whole[(size_t)i] = w;
+    }
+}
+
 inline void build_bvh(const double* centres, const double* radii, int n, BvhHost* out) {
     using namespace bvh_detail;
     out->nodes.clear(); out->leaf_idx.clear();

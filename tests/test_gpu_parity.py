@@ -424,6 +424,35 @@ def test_bvh_sah_build_on_adversarial_scenes(rt, kind):
     assert (oi >= 0).mean() > 0.3
 
 
+def test_scene_update_refit_and_rebuild(rt, book):
+    """rt_update_scene: after the spheres move, a refitted tree (old topology), a rebuilt tree and a fresh upload
+    all give the reference's list-scan answer for the NEW positions, in every scan mode."""
+    c0, r0 = book
+    rng = np.random.default_rng(77)
+    c1 = c0.copy(); r1 = r0.copy()
+    c1[1:] += rng.normal(size=(len(r0) - 1, 3)) * np.array([1.5, 0.05, 1.5])   # shuffle the small spheres around
+    r1[1:] *= rng.uniform(0.5, 1.5, size=len(r0) - 1)
+    n = 8000
+    org = np.tile([[13.0, 2.0, 3.0]], (n, 1)); org[::3] = c1[rng.integers(1, len(r1), size=len(org[::3]))] + [0, 2.0, 0]
+    d = c1[rng.integers(1, len(r1), size=n)] - org + rng.normal(size=(n, 3)) * 0.15   # aimed at the moved spheres
+    oi, orec = ol.hit_batch("orc", c1, r1, org, d)
+    assert (oi > 0).mean() > 0.2
+    from petershirleyraytracer_b200 import scenes
+    cam = scenes.book_camera(64, 40)
+    with rt.Scene(c1, r1) as fresh:
+        ref_img, _, _ = rt.render(fresh, cam, rt.make_params(64, 40, 4, 50, seed=9, scan_mode=2))
+    for refit in (True, False):
+        with rt.Scene(c0, r0) as sc:
+            sc.update(c1, r1, refit=refit)
+            for mode in (0, 1, 2):
+                idx, rec = rt.hit(sc, org, d, scan_mode=mode)
+                assert np.array_equal(idx, oi) and np.array_equal(bits(rec), bits(orec)), (refit, mode)
+            img, _, st = rt.render(sc, cam, rt.make_params(64, 40, 4, 50, seed=9, scan_mode=2))
+            assert np.array_equal(img, ref_img) and st["node_tests"] > 0
+            with pytest.raises(ValueError):
+                sc.update(c1[:-1], r1[:-1])
+
+
 def test_bvh_render_equals_linear_scan(rt, book):
     from petershirleyraytracer_b200 import scenes
     c, r = book
