@@ -223,6 +223,57 @@ inline rt_camera to_abi(const camera& c) {
     return a;
 }
 
+// ---- Scene construction helpers.  The reference ships one hard-coded scene
+// (programs/main.cc:62-63); these build the synthetic BASELINE scenes through the same public API, from a fixed
+// splitmix64 stream, so that the C++ host, the Python binding (scenes.py) and the oracle see identical doubles.
+struct splitmix64 {
+    uint64_t s;
+    explicit splitmix64(uint64_t seed) : s(seed) {}
+    uint64_t next() {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    double u01() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+};
+
+// Book-layout random spheres: ground r = 1000, a jittered grid of r = 0.2 spheres (cells [-g, g)^2), three r = 1
+// spheres.  grid_half = 11 -> 485 spheres (BASELINE configs 3/5); 158 -> ~99.9k (config 4).
+inline hittable_list book_scene(int grid_half = 11, uint64_t seed = 42) {
+    splitmix64 rng(seed);
+    hittable_list world;
+    world.add(make_shared<sphere>(point3(0, -1000, 0), 1000));
+    for (int a = -grid_half; a < grid_half; ++a)
+        for (int b = -grid_half; b < grid_half; ++b) {
+            rng.u01();  // mirrors the book's material draw
+            const double x1 = rng.u01(), x2 = rng.u01();
+            const point3 centre(a + 0.9 * x1, 0.2, b + 0.9 * x2);
+            if ((centre - point3(4, 0.2, 0)).length() > 0.9) world.add(make_shared<sphere>(centre, 0.2));
+        }
+    world.add(make_shared<sphere>(point3(0, 1, 0), 1.0));
+    world.add(make_shared<sphere>(point3(-4, 1, 0), 1.0));
+    world.add(make_shared<sphere>(point3(4, 1, 0), 1.0));
+    return world;
+}
+
+// A positionable pinhole camera expressed through the reference camera's public fields (programs/camera.h:31-35):
+// the class itself is fixed at the origin looking down -z.
+inline camera look_at_camera(const point3& lookfrom, const point3& lookat, const vec3& vup, double vfov_deg, double aspect) {
+    const vec3 w = unit_vector(lookfrom - lookat), u = unit_vector(cross(vup, w)), v = cross(w, u);
+    const double vh = 2.0 * std::tan(degrees_to_radians(vfov_deg) / 2.0), vw = vh * aspect;
+    camera cam;
+    cam.aspect_ratio = aspect;
+    cam.origin = lookfrom;
+    cam.horizontal = vw * u;
+    cam.vertical = vh * v;
+    cam.lower_left_corner = cam.origin - cam.horizontal / 2.0 - cam.vertical / 2.0 - w;
+    return cam;
+}
+inline camera book_camera(int width, int height) {  // lookfrom (13,2,3) -> origin, vfov 20 degrees, no lens
+    return look_at_camera(point3(13, 2, 3), point3(0, 0, 0), vec3(0, 1, 0), 20.0, (double)width / height);
+}
+
 // A world resident on one GPU (owns the rt_scene handle).
 class device_world {
 public:

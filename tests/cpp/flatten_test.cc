@@ -8,6 +8,7 @@
 
 #include <cstdio>
 #include <sstream>
+#include <string>
 
 struct box_like : hittable {
     bool hit(const ray&, double, double, hit_record&) const override { return false; }
@@ -15,7 +16,18 @@ struct box_like : hittable {
 
 #define CHECK(x) do { if (!(x)) { std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #x); return 1; } } while (0)
 
-int main() {
+int main(int argc, char** argv) {
+    if (argc > 1 && std::string(argv[1]) == "book") {  // dump the generated scene + camera for the Python comparison
+        const hittable_list w = rt::book_scene(11, 42);
+        std::vector<double> c, r;
+        rt::flatten(w, c, r);
+        std::printf("%zu\n", r.size());
+        for (size_t k = 0; k < r.size(); ++k) std::printf("%a %a %a %a\n", c[3 * k], c[3 * k + 1], c[3 * k + 2], r[k]);
+        const camera cam = rt::book_camera(1200, 800);
+        const vec3 f[4] = {cam.origin, cam.lower_left_corner, cam.horizontal, cam.vertical};
+        for (const vec3& v : f) std::printf("%a %a %a\n", v.x(), v.y(), v.z());
+        return 0;
+    }
     hittable_list inner;
     inner.add(make_shared<sphere>(point3(1, 2, 3), 0.5));
     inner.add(make_shared<sphere>(point3(4, 5, 6), 1.5));

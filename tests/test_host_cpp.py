@@ -14,3 +14,15 @@ def test_flatten_and_api_surface(tmp_path, rt):
                     f"-Wl,-rpath,{pkg}"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
+
+    # rt::book_scene / rt::book_camera (C++) generate the doubles scenes.py generates
+    import numpy as np
+    from petershirleyraytracer_b200 import scenes
+    lines = subprocess.run([str(exe), "book"], capture_output=True, text=True, check=True).stdout.split("\n")
+    n = int(lines[0])
+    rows = np.array([[float.fromhex(v) for v in ln.split()] for ln in lines[1:1 + n]])
+    c, r = scenes.book_scene(11, 42)
+    assert n == len(r) == 485
+    assert np.array_equal(rows[:, :3], c) and np.array_equal(rows[:, 3], r)
+    cam = np.array([[float.fromhex(v) for v in ln.split()] for ln in lines[1 + n:5 + n]]).reshape(-1)
+    assert np.allclose(cam, scenes.book_camera(1200, 800).as12(), rtol=1e-14, atol=1e-15)
