@@ -473,32 +473,41 @@ __device__ __forceinline__ Best resolve_hits(const SceneDev& sc, bool ovf, int c
     return best;
 }
 
-// One rejection try of programs/vec3.h:87-94 from three 21-bit uniforms: v = -1 + 2*xi (random.h:10-14) is
-// exact, and so is the length test.  Returns true if the point is kept (len^2 <= 1, vec3.h:90).
-__device__ __forceinline__ bool cube_try(uint32_t fx, uint32_t fy, uint32_t fz, double& rx, double& ry, double& rz) {
-    const double s21 = 1.0 / 2097152.0;
-    rx = dadd(-1.0, dmul(2.0, dmul((double)fx, s21)));
-    ry = dadd(-1.0, dmul(2.0, dmul((double)fy, s21)));
-    rz = dadd(-1.0, dmul(2.0, dmul((double)fz, s21)));
-    const double l2 = dadd(dadd(dmul(rx, rx), dmul(ry, ry)), dmul(rz, rz));  // programs/vec3.h:63-66
-    return !(l2 > 1.0);
+// One rejection try of programs/vec3.h:87-94 from three 21-bit uniforms f: v = -1 + 2*(f / 2^21) (random.h:10-14)
+// is exact in FP64, and so are v*v and the sum of the three squares (44 significant bits), so the reference's
+// test len^2 > 1 (vec3.h:90) is decided EXACTLY by integers: with s = f - 2^20, len^2 <= 1 <=> sum s^2 <= 2^40.
+// The tries therefore run on the integer pipe (three IMAD.WIDE, two 64-bit adds, one compare) instead of 17
+// half-rate FP64 instructions each, and only the accepted point is converted to FP64.
+__device__ __forceinline__ bool in_unit_ball(uint32_t fx, uint32_t fy, uint32_t fz) {
+    const int sx = (int)fx - (1 << 20), sy = (int)fy - (1 << 20), sz = (int)fz - (1 << 20);
+    const unsigned long long l2 = (unsigned long long)((long long)sx * sx) + (unsigned long long)((long long)sy * sy) +
+                                  (unsigned long long)((long long)sz * sz);
+    return l2 <= (1ull << 40);
+}
+__device__ __forceinline__ double cube_coord(uint32_t f) {  // -1 + 2 * (f * 2^-21), every step exact
+    return dadd(-1.0, dmul(2.0, dmul((double)f, 1.0 / 2097152.0)));
 }
 
 // programs/vec3.h:83-109 random_in_hemisphere.  One Philox block per bounce: it carries the first TWO tries of
 // the rejection loop as six 21-bit uniforms (the reference's rand() has 15 bits): try A = top 21 bits of words
-// 0,1,2; try B = the low 11 bits of words 0,1,2 extended by 10-bit fields of word 3.  The 5 % of bounces that
-// reject both continue with xorshift128 (Marsaglia 2003) seeded by the block's four words, three outputs per
-// try (top 21 bits each): a cheap continuation instead of further 10-round blocks, since the warp runs as many
-// loop iterations as its unluckiest lane.
+// 0,1,2; try B = the low 11 bits of words 0,1,2 extended by 10-bit fields of word 3.  The 23 % of bounces that
+// reject both (a try is kept with probability pi/6) continue with xorshift128 (Marsaglia 2003) seeded by the
+// block's four words, three outputs per try (top 21 bits each): a cheap continuation instead of further
+// 10-round blocks, since the warp runs as many loop iterations as its unluckiest lane.
 __device__ __forceinline__ void random_in_hemisphere(uint32_t pix, uint32_t smp, uint32_t& blk, uint32_t k0, uint32_t k1,
                                                      double nx, double ny, double nz, double& rx, double& ry,
                                                      double& rz) {
     const uint4 w = philox4x32_10(pix, smp, blk, 0u, k0, k1);
     ++blk;
-    bool ok = cube_try(w.x >> 11, w.y >> 11, w.z >> 11, rx, ry, rz);
-    if (!ok)
-        ok = cube_try(((w.x & 0x7ffu) << 10) | (w.w >> 22), ((w.y & 0x7ffu) << 10) | ((w.w >> 12) & 0x3ffu),
-                      ((w.z & 0x7ffu) << 10) | ((w.w >> 2) & 0x3ffu), rx, ry, rz);
+    uint32_t fx = w.x >> 11, fy = w.y >> 11, fz = w.z >> 11;
+    bool ok = in_unit_ball(fx, fy, fz);
+    {
+        const uint32_t gx = ((w.x & 0x7ffu) << 10) | (w.w >> 22), gy = ((w.y & 0x7ffu) << 10) | ((w.w >> 12) & 0x3ffu),
+                       gz = ((w.z & 0x7ffu) << 10) | ((w.w >> 2) & 0x3ffu);
+        const bool okb = in_unit_ball(gx, gy, gz);
+        fx = ok ? fx : gx; fy = ok ? fy : gy; fz = ok ? fz : gz;
+        ok = ok || okb;
+    }
     if (!ok) {
         uint32_t x0 = w.x, x1 = w.y, x2 = w.z, x3 = w.w;
         if ((x0 | x1 | x2 | x3) == 0u) x0 = 1u;
@@ -513,9 +522,11 @@ __device__ __forceinline__ void random_in_hemisphere(uint32_t pix, uint32_t smp,
                 x0 = t ^ s0 ^ (s0 >> 19);
                 f[i] = x0 >> 11;
             }
-            ok = cube_try(f[0], f[1], f[2], rx, ry, rz);
+            fx = f[0]; fy = f[1]; fz = f[2];
+            ok = in_unit_ball(fx, fy, fz);
         } while (!ok);
     }
+    rx = cube_coord(fx); ry = cube_coord(fy); rz = cube_coord(fz);
     if (!(ddot(rx, ry, rz, nx, ny, nz) > 0)) { rx = -rx; ry = -ry; rz = -rz; }  // programs/vec3.h:105-108
 }
 
