@@ -298,6 +298,33 @@ def test_sharded_tiles_reassemble_to_the_same_frame(rt, book):
             assert np.array_equal(frame.cpu().numpy().reshape(H, W, 4), full), world
 
 
+def test_sharded_progressive_passes(rt, book):
+    """rt_render_pass_device with tile shards: every rank adds its tiles' samples to the frame-ordered accumulator;
+    two passes x three shards leave the sums (and, after the gather, the frame) of one unsharded render."""
+    import torch
+    from petershirleyraytracer_b200 import scenes
+    c, r = book
+    W, H = 150, 100
+    cam = scenes.book_camera(W, H)
+    world = 3
+    with rt.Scene(c, r) as sc:
+        full, sums, _ = rt.render(sc, cam, rt.make_params(W, H, 6, 50, seed=8, early_out=False), want_sums=True)
+        accum = torch.zeros(H * W * 3, dtype=torch.int64, device="cuda")
+        p0 = rt.make_params(W, H, 3, 50, seed=8, early_out=False, shard_rank=0, shard_count=world)
+        L = rt.tile_layout(p0)
+        gathered = torch.zeros(world * L.shard_bytes, dtype=torch.uint8, device="cuda")
+        for begin in (0, 3):
+            for rank in range(world):
+                p = rt.make_params(W, H, 3, 50, seed=8, early_out=False, shard_rank=rank, shard_count=world)
+                rt.render_pass_device(sc, cam, p, begin, accum.data_ptr(), gathered.data_ptr() + rank * L.shard_bytes)
+                rt.render_finish(sc)
+        frame = torch.empty(H * W * 4, dtype=torch.uint8, device="cuda")
+        rt.deinterleave(p0, gathered.data_ptr(), frame.data_ptr(), 0)
+        torch.cuda.synchronize()
+    assert np.array_equal(frame.cpu().numpy().reshape(H, W, 4), full)
+    assert np.array_equal(accum.cpu().numpy().astype(np.float64).reshape(H, W, 3) / 2.0**44, sums)
+
+
 # ------------------------------------------------------------------ C++ host API (include/rt_host.hpp)
 def test_host_main_prints_the_oracle_frame_as_p3(rt, default_scene):
     """petershirleyraytracer_b200/rt_main = the reference's main() shape on the GPU path; its P3 text must be
