@@ -388,7 +388,10 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
                 padz = fabsf(fz) * 2.384185791015625e-07f + 1e-37f;  // 2^-22 |o|: covers the FP32 rounding of o
     const float opx = __fadd_ru(fx, padx), opy = __fadd_ru(fy, pady), opz = __fadd_ru(fz, padz);
     const float omx = __fadd_rd(fx, -padx), omy = __fadd_rd(fy, -pady), omz = __fadd_rd(fz, -padz);
-    const float ivx = (float)(1.0 / dx), ivy = (float)(1.0 / dy), ivz = (float)(1.0 / dz);
+    // 1/d in FP32 (__frcp_rn of the rounded component): 2^-23 relative instead of the 2^-24 of rounding the FP64
+    // quotient -- the products below then carry 4 x 2^-24, inside the 1 +- 2^-19 slack -- and no FP64 division;
+    // +-0 and components beyond the float range give +-inf / +-0 exactly as the rounded FP64 quotient would
+    const float ivx = __frcp_rn((float)dx), ivy = __frcp_rn((float)dy), ivz = __frcp_rn((float)dz);
     float best_up = __double2float_ru(tmax);
     int stack_n[kBvhStack];
     float stack_t[kBvhStack];
