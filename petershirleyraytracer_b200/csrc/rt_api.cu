@@ -382,7 +382,7 @@ int rt_update_scene(rt_scene* sc, const double* centres_xyz, const double* radii
     if (n != sc->n) return fail(RT_ERR_INVALID, "rt_update_scene keeps the sphere count; upload a new scene to change it");
     DeviceGuard guard(sc->device);
     if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
-    if (sc->pending) { RT_CUDA(cudaEventSynchronize(sc->ev1)); sc->pending = false; }
+    if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->ev1));  // (rt_render_finish can still read that render's counters)
     {   // a constant-bank render of the old cull array may still be queued on another stream of this device
         std::lock_guard<std::mutex> lock(g_const_bank.mu);
         cudaEvent_t prev = g_const_bank.last[sc->device & 63];
