@@ -271,7 +271,7 @@ int batch_grid(const rt_scene* sc, int nrays) {
 // topology).  Shared by rt_upload_scene and rt_update_scene.
 int fill_scene(rt_scene* sc, const double* centres_xyz, const double* radii, bool refit) {
     const int n = sc->n;
-    // FP32 cull entries {c, |c|^2 - r^2 - E_k}: computed in FP64, constant term rounded DOWN.
+    // FP32 cull entries {c, -(|c|^2 - r^2 - E_k)}: computed in FP64, constant term rounded DOWN before the negation.
     std::vector<float4> filt((size_t)sc->npad + rt::kScanPad);
     std::vector<double4> exact((size_t)n > 0 ? n : 1);
     std::vector<double> inv_r((size_t)n > 0 ? n : 1);
@@ -283,13 +283,13 @@ int fill_scene(rt_scene* sc, const double* centres_xyz, const double* radii, boo
             const double a2 = cx * cx + cy * cy + cz * cz, r2 = r * r;
             const double Ek = rt::kCullEps * (rt::kCullKc * a2 + rt::kCullKr * r2);
             f.x = (float)cx; f.y = (float)cy; f.z = (float)cz;
-            f.w = round_down_f32(a2 - r2 - Ek);
+            f.w = -round_down_f32(a2 - r2 - Ek);  // stored negated (cull_D adds it)
             if (!(a2 < rt::kCullMaxMag2) || !(r2 < rt::kCullMaxMag2)) sc->cull_ok = false;  // also catches NaN / inf
             exact[k] = make_double4(cx, cy, cz, r);
             inv_r[k] = 1.0 / r;  // IEEE double division on the host == __ddiv_rn(1.0, r)
         } else {
             f.x = f.y = f.z = 0.f;
-            f.w = INFINITY;  // q = +inf -> D = -inf: never passes
+            f.w = -INFINITY;  // D = -inf: never passes
         }
         filt[k] = f;
     }

@@ -28,11 +28,12 @@ constexpr int kNumStats = 10;
 enum StatSlot { ST_SAMPLES = 0, ST_CASTS, ST_SPHERE_TESTS, ST_NODE_TESTS, ST_EXACT_TESTS, ST_BLACK, ST_EARLY_OUTS,
                 ST_PRIMARY_HITS, ST_OVERFLOWS, ST_UNUSED };
 
-// error-bound constants of the FP32 cull (see DESIGN.md "cull error bound"):
-// |D_fp32 - D| <= 2^-24 * (17 (|c|+|o|)^2 + 6 r^2) <= 2^-24 * (34 |c|^2 + 34 |o|^2 + 6 r^2); we fold
-// 2^-24 * (40 |c|^2 + 8 r^2) into the per-sphere constant and 2^-24 * 40 |o|^2 into the per-ray constant.
+// error-bound constants of the FP32 cull (see DESIGN.md "cull error bound"): with S = |c| + |o| and u = 2^-24,
+// |D_fp32 - D| <= u * (19 S^2 + 4 r^2) <= u * (38 |c|^2 + 38 |o|^2 + 4 r^2)  [b: 5uS -> b^2: 10uS^2; inputs of
+// 2o.c: uS^2; four FFMA roundings of magnitudes <= 2S^2 + r^2]; we fold u * (48 |c|^2 + 8 r^2) into the
+// per-sphere constant and u * 48 |o|^2 into the per-ray constant.
 constexpr double kCullEps = 5.9604644775390625e-08;  // 2^-24
-constexpr double kCullKc = 40.0, kCullKr = 8.0, kCullKo = 40.0;
+constexpr double kCullKc = 48.0, kCullKr = 8.0, kCullKo = 48.0;
 // the FP32 cull is used only while |c|^2, r^2 and |o|^2 stay below this (no overflow / NaN in FP32)
 constexpr double kCullMaxMag2 = 1e30;
 
@@ -98,7 +99,7 @@ __device__ __forceinline__ double u32_unit(uint32_t w) { return dmul((double)w, 
 
 // ---------------------------------------------------------------- scene / launch arguments
 struct SceneDev {
-    const float4* filt;    // npad entries {cx, cy, cz, |c|^2 - r^2 - E_k} (FP32 cull), padded with never-pass entries
+    const float4* filt;    // npad entries {cx, cy, cz, -(|c|^2 - r^2 - E_k)} (FP32 cull), padded with never-pass entries
     const double4* exact;  // n entries {cx, cy, cz, r} (FP64, list order)
     const double* inv_r;   // n entries RN(1.0 / r): the reciprocal of programs/vec3.h:151-154, tabulated at upload
     int n, npad;
@@ -172,7 +173,7 @@ __constant__ float4 c_filt[kMaxLinear + kScanPad];
 struct CullRay {  // per-cast constants, 8 registers
     float dx, dy, dz;  // unit direction
     float ndo;         // -(d̂ . o)
-    float mx, my, mz;  // -2 o
+    float mx, my, mz;  // +2 o
     float o2;          // |o|^2 - E_o, rounded down: the pass threshold
 };
 
@@ -186,7 +187,7 @@ __device__ __forceinline__ CullRay make_cull_ray(bool alive, double ox, double o
         const double ux = dx * inv, uy = dy * inv, uz = dz * inv;
         f.dx = (float)ux; f.dy = (float)uy; f.dz = (float)uz;
         f.ndo = (float)(-(ux * ox + uy * oy + uz * oz));
-        f.mx = (float)(-2.0 * ox); f.my = (float)(-2.0 * oy); f.mz = (float)(-2.0 * oz);
+        f.mx = (float)(2.0 * ox); f.my = (float)(2.0 * oy); f.mz = (float)(2.0 * oz);
         const double g2 = ox * ox + oy * oy + oz * oz;
         f.o2 = __double2float_rd(g2 - kCullEps * kCullKo * g2);
     } else {
@@ -197,17 +198,21 @@ __device__ __forceinline__ CullRay make_cull_ray(bool alive, double ox, double o
 }
 
 // The line through (o, d̂) can touch sphere (c, r) only if  (d̂.(c-o))^2 - |c-o|^2 + r^2 >= 0.  Expanded around
-// the world origin this is  b^2 - P >= |o|^2  with b = d̂.c - d̂.o and P = (|c|^2 - r^2) - 2 c.o, i.e. 7
-// FP32-pipe instructions per (ray, sphere): 3 FFMA (b) + 3 FFMA (P, seeded with the per-sphere constant) +
-// 1 FFMA (b*b - P); the per-sphere and per-ray constants carry the error bound, so "pass" is conservative.
+// the world origin this is  b^2 - w + 2 o.c >= |o|^2  with b = d̂.c - d̂.o and w = |c|^2 - r^2, i.e. 7 FP32-pipe
+// instructions per (ray, sphere): 3 FFMA (b), 1 FFMA (b*b - w), 3 FFMA (+ 2 o.c); the per-sphere and per-ray
+// constants carry the error bound, so "pass" is conservative.  The order is chosen so that EVERY FFMA has exactly
+// one per-sphere operand: in the scan those live in uniform registers, an FFMA takes one uniform operand
+// (multiplicand or addend), and a form with two of them (b^2 - (w + ...) seeded with w) costs one extra move of
+// w into a vector register per sphere and lane.
 __device__ __forceinline__ float cull_D(const CullRay& f, const float4 s) {
     float b = fmaf(f.dz, s.z, f.ndo);
     b = fmaf(f.dy, s.y, b);
     b = fmaf(f.dx, s.x, b);
-    float P = fmaf(f.mx, s.x, s.w);
-    P = fmaf(f.my, s.y, P);
-    P = fmaf(f.mz, s.z, P);
-    return fmaf(b, b, -P);  // passes unless this is < f.o2
+    float D = fmaf(b, b, s.w);   // s.w = -(|c|^2 - r^2 - E_k)
+    D = fmaf(f.mx, s.x, D);      // f.m = +2 o
+    D = fmaf(f.my, s.y, D);
+    D = fmaf(f.mz, s.z, D);
+    return D;  // passes unless this is < f.o2
 }
 
 // Scans the npad cull entries (kConst: constant bank, else shared memory) for R rays at once, 12 entries per

@@ -31,8 +31,10 @@ def test_default_render_kernel_scans_on_the_uniform_datapath(rt):
     ldc_vec = len(re.findall(r"LDC(\.\d+)? R\d+, c\[0x3\]\[R", s))
     ffma_ur = len(re.findall(r"FFMA R\d+, [^;]*UR\d+", s))
     ffma = len(re.findall(r"\bFFMA\b", s))
-    assert ldcu >= 16 and ldc_vec <= 8, (ldcu, ldc_vec)
-    assert ffma_ur >= 0.6 * ffma, (ffma_ur, ffma)
+    assert ldcu >= 16 and ldc_vec == 0, (ldcu, ldc_vec)
+    # every FFMA of the cull formula has exactly one per-sphere operand (multiplicand or addend), so none of the
+    # entry constants is moved into a vector register
+    assert ffma_ur >= 0.9 * ffma, (ffma_ur, ffma)
     assert "FMNMX3" in s          # 3-input max of the per-step pass test
     assert "STL" not in s and "LDL" not in s   # no register spills in the hot kernel
 
