@@ -264,11 +264,14 @@ def main():
     host_frame = torch.empty(H * W * 4, dtype=torch.uint8).pin_memory()
 
     def e2e_step(p):
+        t_a = time.perf_counter()
         sc = rt.Scene(wl["centres"], wl["radii"], device=local)      # H2D of the flattened hittable_list
+        t_b = time.perf_counter()
         if world == 1:
             rgba, _, st = rt.render(sc, cam, p)                       # kernel + D2H into a host buffer
             if os.environ.get("RT_BENCH_DEBUG"):
-                print(f"[e2e] kernel {st['kernel_ms']:.1f} ms", file=sys.stderr)
+                print(f"[e2e] upload {1e3 * (t_b - t_a):.1f} ms, render call {1e3 * (time.perf_counter() - t_b):.1f} ms "
+                      f"(kernel {st['kernel_ms']:.1f} ms)", file=sys.stderr)
         else:
             rt.render_device(sc, cam, p, shard.data_ptr(), 0, stream)
             dist.all_gather_into_tensor(gathered, shard)
@@ -276,7 +279,10 @@ def main():
             if rank == 0:
                 host_frame.copy_(frame, non_blocking=False)
             rt.render_finish(sc)
+        t_c = time.perf_counter()
         sc.close()
+        if os.environ.get("RT_BENCH_DEBUG"):
+            print(f"[e2e] close {1e3 * (time.perf_counter() - t_c):.1f} ms", file=sys.stderr)
 
     def e2e_rate(p):
         for _ in range(2):  # untimed: first-use allocator / module initialisation
@@ -285,21 +291,26 @@ def main():
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
+        per_step = []
         for _ in range(args.steps):
             ts = time.perf_counter()
             e2e_step(p)
+            per_step.append(1e3 * (time.perf_counter() - ts))
             if os.environ.get("RT_BENCH_DEBUG"):
-                print(f"[e2e] step {1e3 * (time.perf_counter() - ts):.1f} ms", file=sys.stderr)
+                print(f"[e2e] step {per_step[-1]:.1f} ms", file=sys.stderr)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-        return samples_per_step * args.steps / e2e_s.item() / 1e6
+        # value: all K steps over the whole wall time (max over ranks); the per-step list (rank 0) shows host hiccups
+        return samples_per_step * args.steps / e2e_s.item() / 1e6, [round(x, 1) for x in per_step]
 
-    e2e = {"value": e2e_rate(make(False)), "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
-    e2e_auto = e2e_rate(make(False, rt.SCAN_AUTO))
+    e2e_v, e2e_steps = e2e_rate(make(False))
+    e2e = {"value": e2e_v, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step_rank0": e2e_steps}
+    e2e_auto, e2e_auto_steps = e2e_rate(make(False, rt.SCAN_AUTO))
 
     if rank == 0:
         fma_per_s, _ = rt.measure_fp32_peak(local)
@@ -337,7 +348,7 @@ def main():
                # the same frame, same semantics, through the library's DEFAULT scan mode (RT_SCAN_AUTO -> exact BVH
                # traversal, SAH build at upload): what a caller of rt_render gets without asking for anything
                "auto_mode": {"scan_mode": "RT_SCAN_AUTO (flattened BVH, exact closest-hit semantics)", "value": value_auto,
-                             "e2e": e2e_auto, "unit": "Msamples/s",
+                             "e2e": e2e_auto, "e2e_ms_per_step_rank0": e2e_auto_steps, "unit": "Msamples/s",
                              "box_tests_per_cast": None if not auto_stats else auto_stats["node_tests"] / max(1, auto_stats["casts"]),
                              "fp64_sphere_tests_per_cast": None if not auto_stats else auto_stats["exact_tests"] / max(1, auto_stats["casts"])}}
         print(json.dumps(out), flush=True)
