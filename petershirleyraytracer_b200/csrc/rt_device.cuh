@@ -223,6 +223,8 @@ __device__ __forceinline__ float cull_D(const CullRay& f, const float4 s) {
 // cand[(e*R + r)*stride].  All lanes execute the same instruction stream; the only divergent code is the
 // (rare) append.  Inputs are finite by construction (scene validated at upload, ray checked by the caller),
 // so no value here is NaN.
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
 template <int R, bool kConst>
 __device__ __forceinline__ void cull_scan(const float4* __restrict__ s_filt, int npad, const CullRay (&f)[R],
                                           uint16_t* cand, int stride, int (&cnt)[R], bool (&ovf)[R]) {
@@ -260,9 +262,9 @@ __device__ __forceinline__ void cull_scan(const float4* __restrict__ s_filt, int
         for (int r = 0; r < R; ++r) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) D[r][8 + u] = cull_D(f[r], g2[u]);
-            m[r] = fmaxf(fmaxf(fmaxf(D[r][0], D[r][1]), fmaxf(D[r][2], D[r][3])),
-                         fmaxf(fmaxf(fmaxf(D[r][4], D[r][5]), fmaxf(D[r][6], D[r][7])),
-                               fmaxf(fmaxf(D[r][8], D[r][9]), fmaxf(D[r][10], D[r][11]))));
+            // 12 -> 1 in six 3-input maxima (FMNMX3)
+            m[r] = fmax3(fmax3(fmax3(D[r][0], D[r][1], D[r][2]), fmax3(D[r][3], D[r][4], D[r][5]), fmax3(D[r][6], D[r][7], D[r][8])),
+                         fmax3(D[r][9], D[r][10], D[r][11]), D[r][0]);
             any |= !(m[r] < f[r].o2);
         }
         if (any) {  // some entry of this step may be hit by one of this lane's rays

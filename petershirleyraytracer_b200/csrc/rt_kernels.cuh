@@ -147,7 +147,7 @@ struct RenderTraits {
 #define RT_MINB2 5
 #endif
 #ifndef RT_MINB4
-#define RT_MINB4 2
+#define RT_MINB4 3
 #endif
     static constexpr int kMinBlocks = R >= 4 ? RT_MINB4 : (R == 2 ? RT_MINB2 : RT_MINB1);  // CTAs of 128 threads per SM (register budget)
 };

@@ -26,7 +26,7 @@ if __name__ == "__main__":
     c, r = scenes.book_scene(11)
     cam = scenes.book_camera(1200, 800)
     for smem in (False, True):
-        for ppl in (1, 2):
+        for ppl in (1, 2, 4):
             for eo in (False,):
                 o = run("c3", c, r, cam, 1200, 800, spp, early_out=eo, paths_per_lane=ppl, cull_smem=smem)
                 print("   frac_of_peak(11 slots/test) =", round(o["gtests_s"] * 1e9 * 11 / peak, 4))
