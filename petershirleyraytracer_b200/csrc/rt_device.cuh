@@ -65,14 +65,18 @@ __device__ __forceinline__ RcpA make_rcp(double A) {
     d.rA = __drcp_rn(d.fast ? A : 1.0);
     return d;
 }
+// (out of line: the IEEE division sequence is needed once in a blue moon; inlined at every call site it bloats
+// the hit test with its own branch structure)
+__device__ __noinline__ double ddiv_ieee(double num, double A) { return __ddiv_rn(num, A); }
+
 __device__ __forceinline__ double ddiv_t(double num, const RcpA& d) {
-    const int e = (__double2hiint(num) >> 20) & 0x7ff;
+    const unsigned e = ((unsigned)__double2hiint(num) >> 20) & 0x7ffu;
     const bool zero = num == 0.0;
     // the short form runs for every lane (no branch); only operands outside its range take the subroutine
     const double q0 = __dmul_rn(num, d.rA);
     const double q1 = __fma_rn(__fma_rn(-d.A, q0, num), d.rA, q0);
     double q = __fma_rn(__fma_rn(-d.A, q1, num), d.rA, q1);
-    if (!(d.fast && (zero || (e > 1023 - 700 && e < 1023 + 700)))) q = __ddiv_rn(num, d.A);
+    if (!(d.fast && (zero || (e - 324u) < 1399u))) q = ddiv_ieee(num, d.A);  // exponent outside (-700, 700)
     return (zero && d.fast) ? num : q;  // +-0 / A = +-0 (the short form would lose the sign of -0)
 }
 // programs/vec3.h:156-159: (u0*v0 + u1*v1) + u2*v2
