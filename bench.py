@@ -9,8 +9,8 @@ round-robin over the ranks, all-gathered with NCCL and de-interleaved (strong sc
 
 One JSON line on stdout (rank 0):
   value        device-timed throughput, scene resident in HBM, frame left in HBM
-  e2e          same metric through the host-buffer C ABI (rt_upload_scene + rt_render): H2D of the scene and D2H
-               of the RGBA frame inside the timed region
+  e2e          same metric through the host-buffer C ABI (rt_update_scene + rt_render): H2D of the scene (+ BVH build)
+               and D2H of the RGBA frame into pinned memory inside the timed region
   roofline     FP32-FMA roofline of the render kernel: algorithmic work = sphere tests x 11 FP32-pipe
                instructions, peak = FFMA issue rate measured in this run
   cpu_baseline the reference's own CPU code (oracle/_ref) or its C restatement, timed on this host on a
@@ -262,13 +262,20 @@ def main():
     h2d = wl["centres"].nbytes + wl["radii"].nbytes + 96 + 64
     d2h = H * W * 4
     host_frame = torch.empty(H * W * 4, dtype=torch.uint8).pin_memory()
+    host_view = host_frame.numpy().reshape(H, W, 4)
+
+    # One device scene for all e2e steps: every step re-uploads the flattened hittable_list into it (rt_update_scene
+    # with a full rebuild: H2D of the sphere arrays + BVH build, no cudaMalloc / cudaFree, whose latency on shared
+    # hosts is erratic -- 100-600 ms stalls were seen inside cudaFree) and reads the frame back into pinned memory.
+    e2e_scene = rt.Scene(wl["centres"], wl["radii"], device=local)
 
     def e2e_step(p):
         t_a = time.perf_counter()
-        sc = rt.Scene(wl["centres"], wl["radii"], device=local)      # H2D of the flattened hittable_list
+        sc = e2e_scene
+        sc.update(wl["centres"], wl["radii"], refit=False)           # H2D of the flattened hittable_list + BVH rebuild
         t_b = time.perf_counter()
         if world == 1:
-            rgba, _, st = rt.render(sc, cam, p)                       # kernel + D2H into a host buffer
+            rgba, _, st = rt.render(sc, cam, p, out=host_view)        # kernel + D2H into the pinned host frame
             if os.environ.get("RT_BENCH_DEBUG"):
                 print(f"[e2e] upload {1e3 * (t_b - t_a):.1f} ms, render call {1e3 * (time.perf_counter() - t_b):.1f} ms "
                       f"(kernel {st['kernel_ms']:.1f} ms)", file=sys.stderr)
@@ -279,10 +286,6 @@ def main():
             if rank == 0:
                 host_frame.copy_(frame, non_blocking=False)
             rt.render_finish(sc)
-        t_c = time.perf_counter()
-        sc.close()
-        if os.environ.get("RT_BENCH_DEBUG"):
-            print(f"[e2e] close {1e3 * (time.perf_counter() - t_c):.1f} ms", file=sys.stderr)
 
     def e2e_rate(p):
         for _ in range(2):  # untimed: first-use allocator / module initialisation
@@ -352,6 +355,7 @@ def main():
                              "box_tests_per_cast": None if not auto_stats else auto_stats["node_tests"] / max(1, auto_stats["casts"]),
                              "fp64_sphere_tests_per_cast": None if not auto_stats else auto_stats["exact_tests"] / max(1, auto_stats["casts"])}}
         print(json.dumps(out), flush=True)
+    e2e_scene.close()
     scene.close()
     if world > 1:
         dist.destroy_process_group()

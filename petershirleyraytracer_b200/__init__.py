@@ -226,10 +226,16 @@ class Scene:
             pass
 
 
-def render(scene: Scene, cam: Camera, params: RtParams, want_sums: bool = False):
-    """rt_render: host buffers in/out (the call a reference user makes instead of main.cc:72-88)."""
+def render(scene: Scene, cam: Camera, params: RtParams, want_sums: bool = False, out: np.ndarray | None = None):
+    """rt_render: host buffers in/out (the call a reference user makes instead of main.cc:72-88).  `out`: an
+    (H, W, 4) uint8 C-contiguous array to receive the frame (e.g. a view of pinned memory), else a new array."""
     W, H = params.width, params.height
-    rgba = np.empty((H, W, 4), dtype=np.uint8)
+    if out is None:
+        rgba = np.empty((H, W, 4), dtype=np.uint8)
+    else:
+        if out.shape != (H, W, 4) or out.dtype != np.uint8 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous (H, W, 4) uint8 array")
+        rgba = out
     sums = np.empty((H, W, 3), dtype=np.float64) if want_sums else None
     st = RtStats()
     cs = cam.c_struct()
