@@ -89,7 +89,13 @@ def cpu_reference_rate(wl, target_s: float, threads: int = 0):
     import oracle_lib as ol
     kind = "reference" if ol.have_ref() else "port"
     which = "ref" if kind == "reference" else "orc"
-    cores = (ol.ref().ref_max_threads() if which == "ref" else ol.oracle().orc_max_threads()) if threads == 0 else threads
+    # all the host cores this process may run on -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1,
+    # which would time the reference on one thread
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    cores = avail if threads == 0 else threads
     cam12 = wl["cam"].as12()
     W, H = wl["W"], wl["H"]
     mid = H // 2
