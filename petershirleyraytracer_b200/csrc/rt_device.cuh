@@ -470,31 +470,6 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
     return best;
 }
 
-#ifdef RT_RESOLVE2
-// sphere::hit for sphere k against the caller's FIXED interval [tmin, tmax0], without branches: the root the
-// reference would accept first (near, else far; programs/sphere.cc:23-31) or none.  Merging such "own roots" in
-// list order with  t <= closest_so_far  reproduces hittable_list.cc:9-17 exactly: a near root beyond
-// closest_so_far sends the reference to the far root, which is not smaller, so it rejects either way.
-struct OwnRoot { double t, C; bool ok; };
-__device__ __forceinline__ OwnRoot own_root(const double4* __restrict__ exact, int k, double ox, double oy, double oz,
-                                            double dx, double dy, double dz, const RcpA& dA, double tmin, double tmax0) {
-    const double2 c01 = __ldg(reinterpret_cast<const double2*>(exact + k));
-    const double2 c23 = __ldg(reinterpret_cast<const double2*>(exact + k) + 1);
-    const double amx = dsub(ox, c01.x), amy = dsub(oy, c01.y), amz = dsub(oz, c23.x);
-    const double HALF_B = ddot(dx, dy, dz, amx, amy, amz);
-    OwnRoot r;
-    r.C = dsub(ddot(amx, amy, amz, amx, amy, amz), dmul(c23.y, c23.y));
-    const double disc = dsub(dmul(HALF_B, HALF_B), dmul(dA.A, r.C));
-    const bool hit = !(disc < 0);
-    const double sqrt_d = dsqrt(hit ? disc : 0.0);
-    const double t1 = ddiv_t(dsub(-HALF_B, sqrt_d), dA), t2 = ddiv_t(dadd(-HALF_B, sqrt_d), dA);
-    const bool in1 = !(t1 < tmin || t1 > tmax0), in2 = !(t2 < tmin || t2 > tmax0);
-    r.t = in1 ? t1 : t2;
-    r.ok = hit && (in1 || in2);
-    return r;
-}
-#endif
-
 // hittable_list::hit for one ray given its survivors (or the full list when ovf): list order, shrinking tmax.
 __device__ __forceinline__ Best resolve_hits(const SceneDev& sc, bool ovf, int cnt, const uint16_t* cand, int cand_step,
                                              double ox, double oy, double oz, double dx, double dy, double dz, double A,
@@ -503,28 +478,11 @@ __device__ __forceinline__ Best resolve_hits(const SceneDev& sc, bool ovf, int c
     best.t = tmax; best.C = 1.0; best.k = -1;
     const int n_iter = ovf ? sc.n : cnt;  // candidate list, or every sphere when the list overflowed
     const RcpA dA = make_rcp(A);
-#ifdef RT_RESOLVE2
-    // two candidates per iteration: their FP64 chains are independent, so the pair costs little more latency than
-    // one test, and the loop runs half as many (divergent) iterations
-#pragma unroll 1
-    for (int e = 0; e < n_iter; e += 2) {
-        const bool two = e + 1 < n_iter;
-        int ka = ovf ? e : (int)cand[e * cand_step];
-        int kb = two ? (ovf ? e + 1 : (int)cand[(e + 1) * cand_step]) : ka;
-        const bool va = ka < sc.n, vb = two && kb < sc.n;
-        ka = va ? ka : 0; kb = vb ? kb : ka;
-        const OwnRoot a = own_root(sc.exact, ka, ox, oy, oz, dx, dy, dz, dA, tmin, tmax);
-        const OwnRoot b = own_root(sc.exact, kb, ox, oy, oz, dx, dy, dz, dA, tmin, tmax);
-        if (va && a.ok && a.t <= best.t) { best.t = a.t; best.C = a.C; best.k = ka; }
-        if (vb && b.ok && b.t <= best.t) { best.t = b.t; best.C = b.C; best.k = kb; }
-    }
-#else
 #pragma unroll 1
     for (int e = 0; e < n_iter; ++e) {
         const int k = ovf ? e : (int)cand[e * cand_step];
         if (k < sc.n) exact_test(sc.exact, k, ox, oy, oz, dx, dy, dz, dA, tmin, best);
     }
-#endif
     n_exact += (uint32_t)n_iter;
     return best;
 }
