@@ -125,6 +125,7 @@ def run_reference_arm(args, wl):
     if rank != 0:
         return
     per_step = max(2.0, min(20.0, 150.0 / (args.steps + args.warmup)))
+    per_step = float(os.environ.get("RT_BENCH_REF_SECONDS", per_step))   # (tests shorten the sample)
     vals = []
     for i in range(args.warmup + args.steps):
         r = cpu_reference_rate(wl, per_step)
