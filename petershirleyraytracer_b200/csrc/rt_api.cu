@@ -252,7 +252,7 @@ int finish_render(rt_scene* sc, rt_stats* st) {
     st->kernel_ms = ms;
     st->samples = h[rt::ST_SAMPLES]; st->casts = h[rt::ST_CASTS];
     st->sphere_tests = (sc->last_mode == RT_SCAN_FILTERED) ? h[rt::ST_CASTS] * (uint64_t)sc->n : 0;
-    st->node_tests = 2 * h[rt::ST_NODE_TESTS];  // two child boxes per visited node
+    st->node_tests = 4 * h[rt::ST_NODE_TESTS];  // four child boxes per visited (4-wide) node
     st->exact_tests = h[rt::ST_EXACT_TESTS];
     st->black = h[rt::ST_BLACK]; st->early_outs = h[rt::ST_EARLY_OUTS];
     st->primary_hits = h[rt::ST_PRIMARY_HITS]; st->overflows = h[rt::ST_OVERFLOWS];
@@ -311,14 +311,14 @@ int fill_scene(rt_scene* sc, const double* centres_xyz, const double* radii, boo
         rt::build_bvh(centres_xyz, radii, n, &sc->bvh_host);
     }
     const rt::BvhHost& bvh = sc->bvh_host;
-    const size_t nb = bvh.nodes.size() * sizeof(rt::BvhNode), lb = (bvh.leaf_idx.size() + 1) * sizeof(int32_t);
-    if (!have_tree || (int)bvh.nodes.size() != sc->bvh_nodes) {  // (a rebuild may change the node count)
+    const size_t nb = bvh.nodes4.size() * sizeof(rt::Bvh4Node), lb = (bvh.leaf_idx.size() + 1) * sizeof(int32_t);
+    if (!have_tree || (int)bvh.nodes4.size() != sc->bvh_nodes) {  // (a rebuild may change the node count)
         cudaFree(sc->d_bvh_nodes); cudaFree(sc->d_bvh_leaf);
         sc->d_bvh_nodes = nullptr; sc->d_bvh_leaf = nullptr;
         if (cudaMalloc(&sc->d_bvh_nodes, nb) != cudaSuccess || cudaMalloc(&sc->d_bvh_leaf, lb) != cudaSuccess) return RT_ERR_CUDA;
     }
-    sc->bvh_nodes = (int)bvh.nodes.size();
-    if (cudaMemcpy(sc->d_bvh_nodes, bvh.nodes.data(), nb, cudaMemcpyHostToDevice) != cudaSuccess) return RT_ERR_CUDA;
+    sc->bvh_nodes = (int)bvh.nodes4.size();
+    if (cudaMemcpy(sc->d_bvh_nodes, bvh.nodes4.data(), nb, cudaMemcpyHostToDevice) != cudaSuccess) return RT_ERR_CUDA;
     if (!bvh.leaf_idx.empty() &&
         cudaMemcpy(sc->d_bvh_leaf, bvh.leaf_idx.data(), bvh.leaf_idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess)
         return RT_ERR_CUDA;

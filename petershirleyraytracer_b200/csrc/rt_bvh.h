@@ -25,9 +25,20 @@ static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
 constexpr int kBvhLeafMax = 4;
 
+// The device tree: four children per node (the binary tree with every other level collapsed), boxes in
+// structure-of-arrays form so that one float4 load brings the same bound of all four children.  128 bytes.
+struct Bvh4Node {
+    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
+    int32_t child[4];  // >= 0: node index; < 0: leaf = 0x80000000 | first << 3 | count; kBvhEmpty: no child
+    int32_t pad[4];
+};
+static_assert(sizeof(Bvh4Node) == 128, "Bvh4Node must be 128 bytes");
+constexpr int32_t kBvhEmpty = (int32_t)0x80000000u;
+
 struct BvhHost {
-    std::vector<BvhNode> nodes;     // nodes[0] = root
+    std::vector<BvhNode> nodes;     // binary tree, nodes[0] = root (build / refit work on this one)
     std::vector<int32_t> leaf_idx;  // sphere list indices, leaf by leaf
+    std::vector<Bvh4Node> nodes4;   // collapsed 4-wide tree, nodes4[0] = root (what the device traverses)
 };
 
 namespace bvh_detail {
@@ -191,6 +202,8 @@ struct Builder {
 
 }  // namespace bvh_detail
 
+inline void collapse_bvh4(BvhHost* bvh);
+
 // Refit: same topology (nodes, leaf lists), boxes recomputed for moved / resized spheres.  Children are
 // stored after their parent, so one pass from the last node to the root sees every child box before it is needed.
 // Exactness never depends on the tree's quality, only the traversal cost does; rebuild after large motion.
@@ -223,6 +236,68 @@ inline void refit_bvh(const double* centres, const double* radii, BvhHost* bvh) 
         for (int a = 0; a < 3; ++a) { w.lo[a] = std::min(w.lo[a], b1.lo[a]); w.hi[a] = std::max(w.hi[a], b1.hi[a]); }
         whole[(size_t)i] = w;
     }
+    collapse_bvh4(bvh);  // (derived from the binary tree: same topology unless box areas changed the collapse order)
+}
+
+// Binary -> 4-wide: a node's children are replaced by their own children, largest box first, until four slots are
+// filled or only leaves remain.  Works on the stored (already padded, FP32) child boxes, so the 4-wide boxes are
+// exactly the binary tree's boxes and the conservativeness argument carries over unchanged.
+inline void collapse_bvh4(BvhHost* bvh) {
+    struct Slot { float lo[3], hi[3]; int32_t ref; };
+    auto area = [](const Slot& s) {
+        const double dx = (double)s.hi[0] - s.lo[0], dy = (double)s.hi[1] - s.lo[1], dz = (double)s.hi[2] - s.lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    };
+    auto slots_of = [&](int32_t node, Slot* out) {
+        const BvhNode& b = bvh->nodes[(size_t)node];
+        for (int a = 0; a < 3; ++a) { out[0].lo[a] = b.lo0[a]; out[0].hi[a] = b.hi0[a]; out[1].lo[a] = b.lo1[a]; out[1].hi[a] = b.hi1[a]; }
+        out[0].ref = b.child0; out[1].ref = b.child1;
+    };
+    bvh->nodes4.clear();
+    if (bvh->nodes.empty()) return;
+    std::vector<std::pair<int32_t, int32_t>> todo;  // (binary node, 4-wide node to fill)
+    bvh->nodes4.push_back(Bvh4Node{});
+    todo.push_back({0, 0});
+    while (!todo.empty()) {
+        const auto [bin, me] = todo.back();
+        todo.pop_back();
+        Slot s[4];
+        int ns = 2;
+        slots_of(bin, s);
+        while (ns < 4) {
+            int pick = -1;
+            double best = -1.0;
+            for (int i = 0; i < ns; ++i)
+                if (s[i].ref >= 0) {
+                    const double a = area(s[i]);
+                    if (!(a <= best)) { best = a; pick = i; }  // (NaN-safe: inf - inf areas still get picked)
+                }
+            if (pick < 0) break;
+            Slot two[2];
+            slots_of(s[pick].ref, two);
+            s[pick] = two[0];
+            s[ns++] = two[1];
+        }
+        Bvh4Node n4{};
+        for (int i = 0; i < 4; ++i) {
+            if (i < ns && s[i].ref != kBvhEmpty) {
+                n4.lox[i] = s[i].lo[0]; n4.loy[i] = s[i].lo[1]; n4.loz[i] = s[i].lo[2];
+                n4.hix[i] = s[i].hi[0]; n4.hiy[i] = s[i].hi[1]; n4.hiz[i] = s[i].hi[2];
+                if (s[i].ref >= 0) {
+                    const int32_t child = (int32_t)bvh->nodes4.size();
+                    bvh->nodes4.push_back(Bvh4Node{});
+                    todo.push_back({s[i].ref, child});
+                    n4.child[i] = child;
+                } else {
+                    n4.child[i] = s[i].ref;
+                }
+            } else {
+                n4.lox[i] = n4.loy[i] = n4.loz[i] = INFINITY; n4.hix[i] = n4.hiy[i] = n4.hiz[i] = -INFINITY;
+                n4.child[i] = kBvhEmpty;
+            }
+        }
+        bvh->nodes4[(size_t)me] = n4;
+    }
 }
 
 inline void build_bvh(const double* centres, const double* radii, int n, BvhHost* out) {
@@ -238,9 +313,11 @@ inline void build_bvh(const double* centres, const double* radii, int n, BvhHost
         if (n > 0) store_box(b.bounds(0, n), root.lo0, root.hi0); else empty_box(root.lo0, root.hi0);
         empty_box(root.lo1, root.hi1);
         root.child0 = leaf; root.child1 = (int32_t)0x80000000u;
+        collapse_bvh4(out);
         return;
     }
     b.build(0, n);  // nodes[0] is the root because the first push_back happens at the top call
+    collapse_bvh4(out);
 }
 
 }  // namespace rt

@@ -107,7 +107,7 @@ struct SceneDev {
     const double4* exact;  // n entries {cx, cy, cz, r} (FP64, list order)
     const double* inv_r;   // n entries RN(1.0 / r): the reciprocal of programs/vec3.h:151-154, tabulated at upload
     int n, npad;
-    const float4* bvh_nodes;   // 4 float4 per node (rt_bvh.h: BvhNode), root = node 0; NULL if not built
+    const float4* bvh_nodes;   // 8 float4 per node (rt_bvh.h: Bvh4Node), root = node 0; NULL if not built
     const int32_t* bvh_leaf;   // sphere list indices, leaf by leaf
 };
 
@@ -408,56 +408,60 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
     float stack_t[kBvhStack];
     int sp = 0, node = 0;
     for (;;) {
-        const float4 q0 = __ldg(sc.bvh_nodes + 4 * node), q1 = __ldg(sc.bvh_nodes + 4 * node + 1);
-        const float4 q2 = __ldg(sc.bvh_nodes + 4 * node + 2), q3 = __ldg(sc.bvh_nodes + 4 * node + 3);
+        // one 4-wide node: 128 bytes, the same bound of all four children per float4
+        const float4* nb = sc.bvh_nodes + 8 * node;
+        const float4 qlx = __ldg(nb), qly = __ldg(nb + 1), qlz = __ldg(nb + 2);
+        const float4 qhx = __ldg(nb + 3), qhy = __ldg(nb + 4), qhz = __ldg(nb + 5);
+        const float4 qc = __ldg(nb + 6);
         ++n_nodes;
-        const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-        float tn0, tn1;
-        bool h0, h1;
-        {
-            const float ax = (q0.x - opx) * ivx, bx = (q0.w - omx) * ivx;
-            const float ay = (q0.y - opy) * ivy, by = (q1.x - omy) * ivy;
-            const float az = (q0.z - opz) * ivz, bz = (q1.y - omz) * ivz;
-            tn0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
-            const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-            h0 = tn0 <= tf * kUp && tn0 * kDn <= best_up;
-        }
-        {
-            const float ax = (q1.z - opx) * ivx, bx = (q2.y - omx) * ivx;
-            const float ay = (q1.w - opy) * ivy, by = (q2.z - omy) * ivy;
-            const float az = (q2.x - opz) * ivz, bz = (q2.w - omz) * ivz;
-            tn1 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
-            const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-            h1 = tn1 <= tf * kUp && tn1 * kDn <= best_up;
-        }
-        // leaves are resolved on the spot (the nearer one first), inner children go to the stack
+        const float lx[4] = {qlx.x, qlx.y, qlx.z, qlx.w}, ly[4] = {qly.x, qly.y, qly.z, qly.w}, lz[4] = {qlz.x, qlz.y, qlz.z, qlz.w};
+        const float hx[4] = {qhx.x, qhx.y, qhx.z, qhx.w}, hy[4] = {qhy.x, qhy.y, qhy.z, qhy.w}, hz[4] = {qhz.x, qhz.y, qhz.z, qhz.w};
+        const int ch[4] = {__float_as_int(qc.x), __float_as_int(qc.y), __float_as_int(qc.z), __float_as_int(qc.w)};
+        float tn[4];
+        bool hit[4];
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-            const bool first0 = tn0 <= tn1;
-            const bool use0 = (pass == 0) == first0;
-            const int c = use0 ? c0 : c1;
-            const bool h = use0 ? h0 : h1;
-            const float tn = use0 ? tn0 : tn1;
-            if (h && c < 0 && tn * kDn <= best_up) {
-                const int first = (int)(((unsigned)c & 0x7fffffffu) >> 3), count = c & 7;
-                for (int i = 0; i < count; ++i) {
-                    const int k = __ldg(sc.bvh_leaf + first + i);
+        for (int i = 0; i < 4; ++i) {
+            const float ax = (lx[i] - opx) * ivx, bx = (hx[i] - omx) * ivx;
+            const float ay = (ly[i] - opy) * ivy, by = (hy[i] - omy) * ivy;
+            const float az = (lz[i] - opz) * ivz, bz = (hz[i] - omz) * ivz;
+            tn[i] = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+            const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+            hit[i] = ch[i] != (int)0x80000000 && tn[i] <= tf * kUp && tn[i] * kDn <= best_up;
+        }
+        // hit leaves are resolved on the spot (each re-checked against the best found so far)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (hit[i] && ch[i] < 0 && tn[i] * kDn <= best_up) {
+                const int first = (int)(((unsigned)ch[i] & 0x7fffffffu) >> 3), count = ch[i] & 7;
+                for (int j = 0; j < count; ++j) {
+                    const int k = __ldg(sc.bvh_leaf + first + j);
                     ++n_exact;
                     if (exact_test_unordered(sc.exact, k, ox, oy, oz, dx, dy, dz, dA, tmin, tmax, best))
                         best_up = __double2float_ru(best.t);
                 }
             }
         }
-        const bool in0 = h0 && c0 >= 0 && tn0 * kDn <= best_up, in1 = h1 && c1 >= 0 && tn1 * kDn <= best_up;
-        if (in0 && in1) {
-            const bool near0 = tn0 <= tn1;
-            if (sp >= kBvhStack) { overflow = true; return best; }
-            stack_n[sp] = near0 ? c1 : c0; stack_t[sp] = near0 ? tn1 : tn0; ++sp;
-            node = near0 ? c0 : c1;
-        } else if (in0) {
-            node = c0;
-        } else if (in1) {
-            node = c1;
+        // hit inner children: descend into the nearest, stack the others
+        int next = -1;
+        float next_t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (hit[i] && ch[i] >= 0 && tn[i] * kDn <= best_up) {
+                int pn = ch[i];
+                float pt = tn[i];
+                if (next < 0 || pt < next_t) {   // new nearest: the old one (if any) goes to the stack
+                    const int on = next; const float ot = next_t;
+                    next = pn; next_t = pt;
+                    pn = on; pt = ot;
+                }
+                if (pn >= 0) {
+                    if (sp >= kBvhStack) { overflow = true; return best; }
+                    stack_n[sp] = pn; stack_t[sp] = pt; ++sp;
+                }
+            }
+        }
+        if (next >= 0) {
+            node = next;
         } else {
             bool found = false;
             while (sp > 0) {
