@@ -252,7 +252,7 @@ int finish_render(rt_scene* sc, rt_stats* st) {
     st->kernel_ms = ms;
     st->samples = h[rt::ST_SAMPLES]; st->casts = h[rt::ST_CASTS];
     st->sphere_tests = (sc->last_mode == RT_SCAN_FILTERED) ? h[rt::ST_CASTS] * (uint64_t)sc->n : 0;
-    st->node_tests = 4 * h[rt::ST_NODE_TESTS];  // four child boxes per visited (4-wide) node
+    st->node_tests = rt::kBvhWidth * h[rt::ST_NODE_TESTS];  // child boxes per visited wide node
     st->exact_tests = h[rt::ST_EXACT_TESTS];
     st->black = h[rt::ST_BLACK]; st->early_outs = h[rt::ST_EARLY_OUTS];
     st->primary_hits = h[rt::ST_PRIMARY_HITS]; st->overflows = h[rt::ST_OVERFLOWS];

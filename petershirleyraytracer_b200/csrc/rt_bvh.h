@@ -27,12 +27,16 @@ constexpr int kBvhLeafMax = 4;
 
 // The device tree: four children per node (the binary tree with every other level collapsed), boxes in
 // structure-of-arrays form so that one float4 load brings the same bound of all four children.  128 bytes.
+#ifndef RT_BVH_WIDTH
+#define RT_BVH_WIDTH 4
+#endif
+constexpr int kBvhWidth = RT_BVH_WIDTH;  // children per device node (4 or 8)
 struct Bvh4Node {
-    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
-    int32_t child[4];  // >= 0: node index; < 0: leaf = 0x80000000 | first << 3 | count; kBvhEmpty: no child
-    int32_t pad[4];
+    float lox[kBvhWidth], loy[kBvhWidth], loz[kBvhWidth], hix[kBvhWidth], hiy[kBvhWidth], hiz[kBvhWidth];
+    int32_t child[kBvhWidth];  // >= 0: node index; < 0: leaf = 0x80000000 | first << 3 | count; kBvhEmpty: no child
+    int32_t pad[kBvhWidth];
 };
-static_assert(sizeof(Bvh4Node) == 128, "Bvh4Node must be 128 bytes");
+static_assert(sizeof(Bvh4Node) == 32 * kBvhWidth, "Bvh4Node must be 32 bytes per child");
 constexpr int32_t kBvhEmpty = (int32_t)0x80000000u;
 
 struct BvhHost {
@@ -261,10 +265,10 @@ inline void collapse_bvh4(BvhHost* bvh) {
     while (!todo.empty()) {
         const auto [bin, me] = todo.back();
         todo.pop_back();
-        Slot s[4];
+        Slot s[kBvhWidth];
         int ns = 2;
         slots_of(bin, s);
-        while (ns < 4) {
+        while (ns < kBvhWidth) {
             int pick = -1;
             double best = -1.0;
             for (int i = 0; i < ns; ++i)
@@ -279,7 +283,7 @@ inline void collapse_bvh4(BvhHost* bvh) {
             s[ns++] = two[1];
         }
         Bvh4Node n4{};
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < kBvhWidth; ++i) {
             if (i < ns && s[i].ref != kBvhEmpty) {
                 n4.lox[i] = s[i].lo[0]; n4.loy[i] = s[i].lo[1]; n4.loz[i] = s[i].lo[2];
                 n4.hix[i] = s[i].hi[0]; n4.hiy[i] = s[i].hi[1]; n4.hiz[i] = s[i].hi[2];

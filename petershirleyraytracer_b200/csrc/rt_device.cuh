@@ -107,7 +107,7 @@ struct SceneDev {
     const double4* exact;  // n entries {cx, cy, cz, r} (FP64, list order)
     const double* inv_r;   // n entries RN(1.0 / r): the reciprocal of programs/vec3.h:151-154, tabulated at upload
     int n, npad;
-    const float4* bvh_nodes;   // 8 float4 per node (rt_bvh.h: Bvh4Node), root = node 0; NULL if not built
+    const float4* bvh_nodes;   // 2 float4 per child, kBvhW children per node (rt_bvh.h: Bvh4Node), root = node 0; NULL if not built
     const int32_t* bvh_leaf;   // sphere list indices, leaf by leaf
 };
 
@@ -384,6 +384,10 @@ __device__ __forceinline__ bool exact_test_unordered(const double4* __restrict__
 // here), a subtree is skipped only if it is missed or its entry distance is strictly beyond the current
 // best, and every sphere of a visited leaf runs the FP64 test above.  Requires tmin >= 0 and a finite,
 // non-zero direction (callers route other rays to the sequential scan).  Nearer child first.
+#ifndef RT_BVH_WIDTH
+#define RT_BVH_WIDTH 4
+#endif
+constexpr int kBvhW = RT_BVH_WIDTH;  // children per device BVH node (== rt_bvh.h: kBvhWidth)
 constexpr int kBvhStack = 48;
 __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double oy, double oz, double dx, double dy,
                                          double dz, double A, double tmin, double tmax, uint32_t& n_exact,
@@ -408,19 +412,30 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
     float stack_t[kBvhStack];
     int sp = 0, node = 0;
     for (;;) {
-        // one 4-wide node: 128 bytes, the same bound of all four children per float4
-        const float4* nb = sc.bvh_nodes + 8 * node;
-        const float4 qlx = __ldg(nb), qly = __ldg(nb + 1), qlz = __ldg(nb + 2);
-        const float4 qhx = __ldg(nb + 3), qhy = __ldg(nb + 4), qhz = __ldg(nb + 5);
-        const float4 qc = __ldg(nb + 6);
-        ++n_nodes;
-        const float lx[4] = {qlx.x, qlx.y, qlx.z, qlx.w}, ly[4] = {qly.x, qly.y, qly.z, qly.w}, lz[4] = {qlz.x, qlz.y, qlz.z, qlz.w};
-        const float hx[4] = {qhx.x, qhx.y, qhx.z, qhx.w}, hy[4] = {qhy.x, qhy.y, qhy.z, qhy.w}, hz[4] = {qhz.x, qhz.y, qhz.z, qhz.w};
-        const int ch[4] = {__float_as_int(qc.x), __float_as_int(qc.y), __float_as_int(qc.z), __float_as_int(qc.w)};
-        float tn[4];
-        bool hit[4];
+        // one wide node (32 bytes per child), structure of arrays: the same bound of four children per float4
+        constexpr int W = kBvhW, Q = kBvhW / 4;
+        const float4* nb = sc.bvh_nodes + 8 * Q * node;
+        float lx[W], ly[W], lz[W], hx[W], hy[W], hz[W];
+        int ch[W];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int q = 0; q < Q; ++q) {
+            const float4 a0 = __ldg(nb + 0 * Q + q), a1 = __ldg(nb + 1 * Q + q), a2 = __ldg(nb + 2 * Q + q);
+            const float4 a3 = __ldg(nb + 3 * Q + q), a4 = __ldg(nb + 4 * Q + q), a5 = __ldg(nb + 5 * Q + q);
+            const float4 a6 = __ldg(nb + 6 * Q + q);
+            lx[4 * q] = a0.x; lx[4 * q + 1] = a0.y; lx[4 * q + 2] = a0.z; lx[4 * q + 3] = a0.w;
+            ly[4 * q] = a1.x; ly[4 * q + 1] = a1.y; ly[4 * q + 2] = a1.z; ly[4 * q + 3] = a1.w;
+            lz[4 * q] = a2.x; lz[4 * q + 1] = a2.y; lz[4 * q + 2] = a2.z; lz[4 * q + 3] = a2.w;
+            hx[4 * q] = a3.x; hx[4 * q + 1] = a3.y; hx[4 * q + 2] = a3.z; hx[4 * q + 3] = a3.w;
+            hy[4 * q] = a4.x; hy[4 * q + 1] = a4.y; hy[4 * q + 2] = a4.z; hy[4 * q + 3] = a4.w;
+            hz[4 * q] = a5.x; hz[4 * q + 1] = a5.y; hz[4 * q + 2] = a5.z; hz[4 * q + 3] = a5.w;
+            ch[4 * q] = __float_as_int(a6.x); ch[4 * q + 1] = __float_as_int(a6.y);
+            ch[4 * q + 2] = __float_as_int(a6.z); ch[4 * q + 3] = __float_as_int(a6.w);
+        }
+        ++n_nodes;
+        float tn[W];
+        bool hit[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
             const float ax = (lx[i] - opx) * ivx, bx = (hx[i] - omx) * ivx;
             const float ay = (ly[i] - opy) * ivy, by = (hy[i] - omy) * ivy;
             const float az = (lz[i] - opz) * ivz, bz = (hz[i] - omz) * ivz;
@@ -430,7 +445,7 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
         }
         // hit leaves are resolved on the spot (each re-checked against the best found so far)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < W; ++i) {
             if (hit[i] && ch[i] < 0 && tn[i] * kDn <= best_up) {
                 const int first = (int)(((unsigned)ch[i] & 0x7fffffffu) >> 3), count = ch[i] & 7;
                 for (int j = 0; j < count; ++j) {
@@ -445,7 +460,7 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
         int next = -1;
         float next_t = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < W; ++i) {
             if (hit[i] && ch[i] >= 0 && tn[i] * kDn <= best_up) {
                 int pn = ch[i];
                 float pt = tn[i];
