@@ -23,7 +23,10 @@ struct BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
-constexpr int kBvhLeafMax = 4;
+#ifndef RT_BVH_LEAF
+#define RT_BVH_LEAF 2
+#endif
+constexpr int kBvhLeafMax = RT_BVH_LEAF;  // spheres per leaf (the leaf reference holds a 3-bit count)
 
 // The device tree: four children per node (the binary tree with every other level collapsed), boxes in
 // structure-of-arrays form so that one float4 load brings the same bound of all four children.  128 bytes.
