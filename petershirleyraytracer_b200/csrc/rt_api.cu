@@ -112,10 +112,10 @@ void tile_layout(const rt_params* p, rt_tile_layout* L) {
     L->shard_bytes = (int64_t)L->tiles_per_shard * rt::kTilePix * 4;
 }
 
-// AUTO: the BVH traversal wherever a BVH was built.  With the SAH build it is at least as fast as the linear
-// cull scan at every scene size measured on B200 (tools/mode_compare.py: 2 spheres 1005 vs 978 Msamples/s, 40:
-// 612 vs 602, 145: 466 vs 395, 485: 360 vs 194, 1939: 331 vs 42); below 16 spheres, where the two are equal, the
-// scan is kept (one scan step, no tree).
+// AUTO: the BVH traversal wherever a BVH was built.  With the 4-wide SAH build it is faster than the linear cull
+// scan from 40 spheres up on B200 (tools/mode_compare.py, profiles/r1_mode_compare.txt: 40: 704 vs 630 Msamples/s,
+// 145: 573 vs 419, 485: 420 vs 206, 1939: 392 vs 45); for a handful of spheres (2: 968 vs 1031) the scan's single
+// step wins, so the scan is kept below 16.
 int resolve_scan_mode(const rt_scene* sc, int mode, int* out) {
     if (mode == RT_SCAN_AUTO) mode = (!sc->cull_ok) ? RT_SCAN_EXACT : (sc->n < 16 ? RT_SCAN_FILTERED : RT_SCAN_BVH);
     if (mode == RT_SCAN_FILTERED && !sc->cull_ok)
