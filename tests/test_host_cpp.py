@@ -26,3 +26,14 @@ def test_flatten_and_api_surface(tmp_path, rt):
     assert np.array_equal(rows[:, :3], c) and np.array_equal(rows[:, 3], r)
     cam = np.array([[float.fromhex(v) for v in ln.split()] for ln in lines[1 + n:5 + n]]).reshape(-1)
     assert np.allclose(cam, scenes.book_camera(1200, 800).as12(), rtol=1e-14, atol=1e-15)
+
+
+def test_bvh_builder_invariants(tmp_path):
+    """rt_bvh.h on the host: each sphere in exactly one leaf, every (padded FP32) box holds the spheres below it -- the
+    property the exact traversal rests on -- for SAH builds of ordinary and adversarial scenes and after a refit."""
+    exe = tmp_path / "bvh_host_test"
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-O1", "-std=c++17", "-I", os.path.join(REPO, "petershirleyraytracer_b200", "csrc"),
+                    os.path.join(REPO, "tests", "cpp", "bvh_host_test.cc"), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout[-2000:] + out.stderr[-2000:]
