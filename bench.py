@@ -341,7 +341,7 @@ def main():
                             "instructions x 2 flop / render-kernel time (CUDA events, avg over the timed launches, per GPU); "
                             "peak = FFMA rate measured in this run by rt_measure_fp32_peak (MEASURED_PEAKS.json has no FP32 "
                             f"figure; nominal 148 SMs x 128 lanes x 1.965 GHz x 2 = 74.4); the kernel itself issues "
-                            "7 FMA-pipe + ~3 other slots per test",
+                            "7 FMA-pipe + ~1.9 other instructions per test in the scan loop",
                     "sphere_tests_per_step": tests_per_step, "casts_per_sample": casts_per_step / samples_per_step,
                     "kernel_ms_per_step": kern_ms / args.steps,
                     "with_early_out": {"msamples_s": value_eo, "casts_per_sample": None if eo_stats is None else
