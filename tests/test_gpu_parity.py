@@ -491,6 +491,21 @@ def test_bvh_render_equals_linear_scan(rt, book):
     assert st["casts"] == bst["casts"] and st["black"] == bst["black"] and st["node_tests"] > 0
 
 
+def test_cull_and_boxes_are_conservative_at_scale(rt, book):
+    """A hundred million casts through the FP32 cull scan and through the 4-wide BVH must leave the same integer
+    radiance sums and counters: one sphere wrongly culled, or one box wrongly skipped, on any cast would show."""
+    from petershirleyraytracer_b200 import scenes
+    c, r = book
+    W, H, spp = 600, 400, 16
+    cam = scenes.book_camera(W, H)
+    with rt.Scene(c, r) as sc:
+        a_acc, a_img, a_st = rt.render_pass(sc, cam, rt.make_params(W, H, spp, 50, seed=11, early_out=False, scan_mode=0), 0)
+        b_acc, b_img, b_st = rt.render_pass(sc, cam, rt.make_params(W, H, spp, 50, seed=11, early_out=False, scan_mode=2), 0)
+    assert a_st["casts"] > 90_000_000
+    assert a_st["casts"] == b_st["casts"] and a_st["black"] == b_st["black"] and a_st["primary_hits"] == b_st["primary_hits"]
+    assert np.array_equal(a_acc, b_acc) and np.array_equal(a_img, b_img)
+
+
 def test_bvh_100k_spheres_config4(rt):
     """BASELINE config 4 scene (~99.9k spheres): primary hits vs the oracle's list scan, and a small render vs
     the FP64-everything mode."""
