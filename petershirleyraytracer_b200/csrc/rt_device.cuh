@@ -407,6 +407,17 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
     // quotient -- the products below then carry 4 x 2^-24, inside the 1 +- 2^-19 slack -- and no FP64 division;
     // +-0 and components beyond the float range give +-inf / +-0 exactly as the rounded FP64 quotient would
     const float ivx = __frcp_rn((float)dx), ivy = __frcp_rn((float)dy), ivz = __frcp_rn((float)dz);
+    // Slab distances as ONE FFMA per plane: (plane - o) * iv = fma(plane, iv, -(o * iv)).  The constant -(o*iv) is
+    // formed exactly in FP64 (24 x 24 bits) and rounded in the direction that keeps the plane's role conservative:
+    // for iv > 0 the lo planes give the near distance (must not be overestimated: round down) and the hi planes the
+    // far distance (round up); for iv < 0 the roles swap.  The FFMA's own rounding is relative to its result and is
+    // covered by the 1 +- 2^-19 factors like before.  An axis with iv = +-inf yields inf - inf = NaN for both planes,
+    // which fminf/fmaxf drop: that axis then does not constrain the interval (conservative).
+    const double pxl = -((double)opx * (double)ivx), pyl = -((double)opy * (double)ivy), pzl = -((double)opz * (double)ivz);
+    const double pxh = -((double)omx * (double)ivx), pyh = -((double)omy * (double)ivy), pzh = -((double)omz * (double)ivz);
+    const float clx = ivx > 0.f ? __double2float_rd(pxl) : __double2float_ru(pxl), chx = ivx > 0.f ? __double2float_ru(pxh) : __double2float_rd(pxh);
+    const float cly = ivy > 0.f ? __double2float_rd(pyl) : __double2float_ru(pyl), chy = ivy > 0.f ? __double2float_ru(pyh) : __double2float_rd(pyh);
+    const float clz = ivz > 0.f ? __double2float_rd(pzl) : __double2float_ru(pzl), chz = ivz > 0.f ? __double2float_ru(pzh) : __double2float_rd(pzh);
     float best_up = __double2float_ru(tmax);
     int stack_n[kBvhStack];
     float stack_t[kBvhStack];
@@ -436,9 +447,9 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
         bool hit[W];
 #pragma unroll
         for (int i = 0; i < W; ++i) {
-            const float ax = (lx[i] - opx) * ivx, bx = (hx[i] - omx) * ivx;
-            const float ay = (ly[i] - opy) * ivy, by = (hy[i] - omy) * ivy;
-            const float az = (lz[i] - opz) * ivz, bz = (hz[i] - omz) * ivz;
+            const float ax = fmaf(lx[i], ivx, clx), bx = fmaf(hx[i], ivx, chx);
+            const float ay = fmaf(ly[i], ivy, cly), by = fmaf(hy[i], ivy, chy);
+            const float az = fmaf(lz[i], ivz, clz), bz = fmaf(hz[i], ivz, chz);
             tn[i] = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
             const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
             hit[i] = ch[i] != (int)0x80000000 && tn[i] <= tf * kUp && tn[i] * kDn <= best_up;
