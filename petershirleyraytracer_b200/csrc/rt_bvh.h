@@ -299,7 +299,9 @@ inline void collapse_bvh4(BvhHost* bvh) {
                     n4.child[i] = s[i].ref;
                 }
             } else {
-                n4.lox[i] = n4.loy[i] = n4.loz[i] = INFINITY; n4.hix[i] = n4.hiy[i] = n4.hiz[i] = -INFINITY;
+                // an empty slot carries NaN bounds: its slab distances are NaN, the far distance stays NaN through
+                // fminf, and `tn <= tf` is false -- the device needs no separate emptiness test
+                n4.lox[i] = n4.loy[i] = n4.loz[i] = NAN; n4.hix[i] = n4.hiy[i] = n4.hiz[i] = NAN;
                 n4.child[i] = kBvhEmpty;
             }
         }

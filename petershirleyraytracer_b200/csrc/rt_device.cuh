@@ -397,7 +397,7 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
     const RcpA dA = make_rcp(A);
     // (An FP32 line test per leaf sphere before the FP64 test was measured: exact tests/cast 4.96 -> 1.21,
     //  but 6 % slower overall -- the per-cast cull constants cost more than the FP64 tests they save.)
-    const float kUp = 1.0f + 1.9073486328125e-06f, kDn = 1.0f - 1.9073486328125e-06f;  // 1 +- 2^-19
+    const float kUp = 1.0f + 1.9073486328125e-06f;  // 1 + 2^-19
     const float fx = (float)ox, fy = (float)oy, fz = (float)oz;
     const float padx = fabsf(fx) * 2.384185791015625e-07f + 1e-37f, pady = fabsf(fy) * 2.384185791015625e-07f + 1e-37f,
                 padz = fabsf(fz) * 2.384185791015625e-07f + 1e-37f;  // 2^-22 |o|: covers the FP32 rounding of o
@@ -418,7 +418,10 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
     const float clx = ivx > 0.f ? __double2float_rd(pxl) : __double2float_ru(pxl), chx = ivx > 0.f ? __double2float_ru(pxh) : __double2float_rd(pxh);
     const float cly = ivy > 0.f ? __double2float_rd(pyl) : __double2float_ru(pyl), chy = ivy > 0.f ? __double2float_ru(pyh) : __double2float_rd(pyh);
     const float clz = ivz > 0.f ? __double2float_rd(pzl) : __double2float_ru(pzl), chz = ivz > 0.f ? __double2float_ru(pzh) : __double2float_rd(pzh);
-    float best_up = __double2float_ru(tmax);
+    // the pruning bound: entry distance tn may matter iff tn * (1 - 2^-19) <= RU(best t); kept pre-divided (rounded
+    // up, so the test only gets looser) so that a box costs one compare against it
+    const float kInvDn = 1.0f + 3.814697265625e-06f;  // > 1 / (1 - 2^-19)
+    float bu = __fmul_ru(__double2float_ru(tmax), kInvDn);
     int stack_n[kBvhStack];
     float stack_t[kBvhStack];
     int sp = 0, node = 0;
@@ -452,18 +455,18 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
             const float az = fmaf(lz[i], ivz, clz), bz = fmaf(hz[i], ivz, chz);
             tn[i] = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
             const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-            hit[i] = ch[i] != (int)0x80000000 && tn[i] <= tf * kUp && tn[i] * kDn <= best_up;
+            hit[i] = tn[i] <= tf * kUp && tn[i] <= bu;   // (empty slots carry NaN boxes: tf = NaN, never hit)
         }
         // hit leaves are resolved on the spot (each re-checked against the best found so far)
 #pragma unroll
         for (int i = 0; i < W; ++i) {
-            if (hit[i] && ch[i] < 0 && tn[i] * kDn <= best_up) {
+            if (hit[i] && ch[i] < 0 && tn[i] <= bu) {
                 const int first = (int)(((unsigned)ch[i] & 0x7fffffffu) >> 3), count = ch[i] & 7;
                 for (int j = 0; j < count; ++j) {
                     const int k = __ldg(sc.bvh_leaf + first + j);
                     ++n_exact;
                     if (exact_test_unordered(sc.exact, k, ox, oy, oz, dx, dy, dz, dA, tmin, tmax, best))
-                        best_up = __double2float_ru(best.t);
+                        bu = __fmul_ru(__double2float_ru(best.t), kInvDn);
                 }
             }
         }
@@ -472,7 +475,7 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
         float next_t = 0.f;
 #pragma unroll
         for (int i = 0; i < W; ++i) {
-            if (hit[i] && ch[i] >= 0 && tn[i] * kDn <= best_up) {
+            if (hit[i] && ch[i] >= 0 && tn[i] <= bu) {
                 int pn = ch[i];
                 float pt = tn[i];
                 if (next < 0 || pt < next_t) {   // new nearest: the old one (if any) goes to the stack
@@ -492,7 +495,7 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
             bool found = false;
             while (sp > 0) {
                 --sp;
-                if (stack_t[sp] * kDn <= best_up) { node = stack_n[sp]; found = true; break; }
+                if (stack_t[sp] <= bu) { node = stack_n[sp]; found = true; break; }
             }
             if (!found) break;
         }
