@@ -9,7 +9,8 @@ W, H = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (1200, 800
 ppl = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 smem = bool(int(sys.argv[6])) if len(sys.argv) > 6 else False
 mode = int(sys.argv[7]) if len(sys.argv) > 7 else 0
-c, r = scenes.book_scene(11)
+grid = int(sys.argv[8]) if len(sys.argv) > 8 else 11   # 11 -> 485 spheres, 158 -> 99 856 (BASELINE config 4)
+c, r = scenes.book_scene(grid)
 cam = scenes.book_camera(W, H)
 with rt.Scene(c, r) as sc:
     p = rt.make_params(W, H, spp, 50, seed=1, early_out=eo, paths_per_lane=ppl, cull_smem=smem, scan_mode=mode)
