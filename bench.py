@@ -37,7 +37,7 @@ SLOTS_PER_TEST = 11  # 3 FADD + 2 FMUL + 6 FFMA of programs/sphe
 
 def workload(name: str, spp_override: int | None):
     from petershirleyraytracer_b200 import scenes
-    key = {"c1": "c1_default", "c3": "c3_book_1200x800", "c5": "c5_book_4k"}.get(name, name)
+    key = {"c1": "c1_default", "c3": "c3_book_1200x800", "c4": "c4_bvh_1920x1080", "c5": "c5_book_4k"}.get(name, name)
     scene_fn, cam_fn, W, H, spp, depth = scenes.CONFIGS[key]
     if spp_override:
         spp = spp_override
@@ -194,7 +194,14 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     frame = torch.empty(H * W * 4, dtype=torch.uint8, device=dev)
 
-    def make(early_out, scan_mode=rt.SCAN_FILTERED):
+    # scenes beyond the linear scan's 4080 spheres (BASELINE config 4) are benchmarked through the BVH; their roofline
+    # counts the executed box tests (14 FP32-pipe slots each: 6 FFMA + 8 min/max/compare) and sphere tests (11)
+    big = len(wl["radii"]) > 4080
+    SLOTS_PER_BOX = 14
+
+    def make(early_out, scan_mode=None):
+        if scan_mode is None:
+            scan_mode = rt.SCAN_BVH if big else rt.SCAN_FILTERED
         # headline = the linear cull-scan kernel BASELINE.json's north_star specifies for this config (its metric,
         # % of the FP32-FMA roofline, is defined on the scan); the library's default AUTO mode (exact BVH
         # traversal) is timed too, device-side and end to end, and reported as "auto_mode"
@@ -251,7 +258,8 @@ def main():
     value = samples_per_step * args.steps / (tot_ms * 1e-3) / 1e6
 
     # per-rank counters -> whole-job sums for the roofline
-    cnt = torch.tensor([stats["sphere_tests"], stats["casts"], stats["samples"], stats["exact_tests"]], dtype=torch.float64, device=dev)
+    slots = (stats["node_tests"] * SLOTS_PER_BOX + stats["exact_tests"] * SLOTS_PER_TEST) if big else stats["sphere_tests"] * SLOTS_PER_TEST
+    cnt = torch.tensor([slots / SLOTS_PER_TEST, stats["casts"], stats["samples"], stats["exact_tests"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(cnt)
     tests_per_step, casts_per_step = cnt[0].item(), cnt[1].item()
@@ -342,17 +350,18 @@ def main():
                             "peak = FFMA rate measured in this run by rt_measure_fp32_peak (MEASURED_PEAKS.json has no FP32 "
                             f"figure; nominal 148 SMs x 128 lanes x 1.965 GHz x 2 = 74.4); the kernel itself issues "
                             "7 FMA-pipe + ~1.9 other instructions per test in the scan loop",
-                    "sphere_tests_per_step": tests_per_step, "casts_per_sample": casts_per_step / samples_per_step,
+                    "sphere_tests_per_step": tests_per_step,   # (BVH workloads: executed box + sphere test slots / 11) "casts_per_sample": casts_per_step / samples_per_step,
                     "kernel_ms_per_step": kern_ms / args.steps,
                     "with_early_out": {"msamples_s": value_eo, "casts_per_sample": None if eo_stats is None else
                                        eo_stats["casts"] * world / samples_per_step}}
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not big:   # (the reference's O(N) scan of 1e5 spheres: ~1 ms per cast)
             cpu = cpu_reference_rate(wl, 12.0)
         out = {"metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "f64 hit/shading + f32 cull", "data": "synthetic",
-               "config": config_dict(wl, args, extra={"early_out": False, "paths_per_lane": 2, "scan_mode": "linear cull scan (RT_SCAN_FILTERED)",
+               "config": config_dict(wl, args, extra={"early_out": False, "paths_per_lane": 1 if big else 2,
+                                                      "scan_mode": "4-wide BVH (RT_SCAN_BVH)" if big else "linear cull scan (RT_SCAN_FILTERED)",
                                                       "value_with_exact_early_out": value_eo}),
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                # the same frame, same semantics, through the library's DEFAULT scan mode (RT_SCAN_AUTO -> exact BVH
