@@ -24,7 +24,7 @@ struct BvhNode {
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
 #ifndef RT_BVH_LEAF
-#define RT_BVH_LEAF 2
+#define RT_BVH_LEAF 1
 #endif
 constexpr int kBvhLeafMax = RT_BVH_LEAF;  // spheres per leaf (the leaf reference holds a 3-bit count)
 

@@ -387,6 +387,9 @@ __device__ __forceinline__ bool exact_test_unordered(const double4* __restrict__
 #ifndef RT_BVH_WIDTH
 #define RT_BVH_WIDTH 4
 #endif
+#ifndef RT_BVH_LEAF
+#define RT_BVH_LEAF 1   // spheres per leaf (== rt_bvh.h: kBvhLeafMax)
+#endif
 constexpr int kBvhW = RT_BVH_WIDTH;  // children per device BVH node (== rt_bvh.h: kBvhWidth)
 constexpr int kBvhStack = 48;
 __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double oy, double oz, double dx, double dy,
@@ -462,12 +465,22 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
         for (int i = 0; i < W; ++i) {
             if (hit[i] && ch[i] < 0 && tn[i] <= bu) {
                 const int first = (int)(((unsigned)ch[i] & 0x7fffffffu) >> 3), count = ch[i] & 7;
+#if RT_BVH_LEAF == 1
+                {   // single-sphere leaves: no loop over the leaf (its branch overhead was ~4 % of the traversal)
+                    (void)count;
+                    const int k = __ldg(sc.bvh_leaf + first);
+                    ++n_exact;
+                    if (exact_test_unordered(sc.exact, k, ox, oy, oz, dx, dy, dz, dA, tmin, tmax, best))
+                        bu = __fmul_ru(__double2float_ru(best.t), kInvDn);
+                }
+#else
                 for (int j = 0; j < count; ++j) {
                     const int k = __ldg(sc.bvh_leaf + first + j);
                     ++n_exact;
                     if (exact_test_unordered(sc.exact, k, ox, oy, oz, dx, dy, dz, dA, tmin, tmax, best))
                         bu = __fmul_ru(__double2float_ru(best.t), kInvDn);
                 }
+#endif
             }
         }
         // hit inner children: descend into the nearest, stack the others
