@@ -171,6 +171,11 @@ struct Builder {
 
     // returns the child reference for spheres order[first, first+count)
     int32_t build(int first, int count, int depth = 0) {
+        if (kBvhLeafMax == 1 && count == 1) {
+            // single-sphere leaves name their sphere directly (leaf_idx is the identity): the device skips the
+            // leaf-list load, a dependent fetch in front of every FP64 sphere test
+            return (int32_t)(0x80000000u | ((uint32_t)order[first] << 3) | 1u);
+        }
         if (count <= kBvhLeafMax) {
             const int32_t at = (int32_t)out->leaf_idx.size();
             // inside a leaf keep list order (not required for correctness; keeps tests readable)
@@ -315,6 +320,10 @@ inline void build_bvh(const double* centres, const double* radii, int n, BvhHost
     Builder b{centres, radii, {}, out};
     b.order.resize(n);
     for (int i = 0; i < n; ++i) b.order[i] = i;
+    if (kBvhLeafMax == 1) {  // identity leaf list (see Builder::build)
+        out->leaf_idx.resize(n);
+        for (int i = 0; i < n; ++i) out->leaf_idx[i] = i;
+    }
     if (n <= kBvhLeafMax) {  // root must be a node: one real leaf + one empty child
         out->nodes.push_back(BvhNode{});
         const int32_t leaf = n > 0 ? b.build(0, n) : (int32_t)0x80000000u;

@@ -468,7 +468,7 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
 #if RT_BVH_LEAF == 1
                 {   // single-sphere leaves: no loop over the leaf (its branch overhead was ~4 % of the traversal)
                     (void)count;
-                    const int k = __ldg(sc.bvh_leaf + first);
+                    const int k = first;   // (single-sphere leaves carry the sphere index itself, rt_bvh.h)
                     ++n_exact;
                     if (exact_test_unordered(sc.exact, k, ox, oy, oz, dx, dy, dz, dA, tmin, tmax, best))
                         bu = __fmul_ru(__double2float_ru(best.t), kInvDn);
