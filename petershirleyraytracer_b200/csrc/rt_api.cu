@@ -113,9 +113,9 @@ void tile_layout(const rt_params* p, rt_tile_layout* L) {
 }
 
 // AUTO: the BVH traversal wherever a BVH was built.  With the 4-wide SAH build it is faster than the linear cull
-// scan from 40 spheres up on B200 (tools/mode_compare.py, profiles/r1_mode_compare.txt: 40: 704 vs 630 Msamples/s,
-// 145: 573 vs 419, 485: 420 vs 206, 1939: 392 vs 45); for a handful of spheres (2: 968 vs 1031) the scan's single
-// step wins, so the scan is kept below 16.
+// scan from 40 spheres up on B200 (tools/mode_compare.py, profiles/r1_mode_compare.txt: 40: 695 vs 631 Msamples/s,
+// 145: 576 vs 419, 485: 466 vs 208, 1939: 442 vs 45); for a handful of spheres the two tie (2: 1033 vs 1013) and the
+// scan's single step needs no tree, so the scan is kept below 16.
 int resolve_scan_mode(const rt_scene* sc, int mode, int* out) {
     if (mode == RT_SCAN_AUTO) mode = (!sc->cull_ok) ? RT_SCAN_EXACT : (sc->n < 16 ? RT_SCAN_FILTERED : RT_SCAN_BVH);
     if (mode == RT_SCAN_FILTERED && !sc->cull_ok)
