@@ -19,9 +19,25 @@
  *   - spheres keep list order: index k here == position k in hittable_list::objects
  *     (programs/hittable_list.h:40); ties in t go to the LATER index, as in programs/hittable_list.cc:11-15.
  *   - random numbers: Philox4x32-10, key = seed, counter = (pixel id, sample, block, 0) with pixel id =
- *     j*W + i (j counted from the bottom like the reference).  Block 0 holds the two jitter draws of
- *     programs/main.cc:80-81; every try of vec3::random_in_unit_sphere (programs/vec3.h:83-95) takes the
- *     next block (x,y,z = words 0,1,2).  Replaces the global rand() stream of programs/random.h:4-8.
+ *     j*W + i (j counted from the bottom like the reference).  Replaces the global rand() stream of
+ *     programs/random.h:4-8.  The stream, exactly (an independent implementation must reproduce it to get
+ *     the same frames; the CPU checker used by this repository's tests does):
+ *       block 0 of a (pixel, sample): the jitter draws of programs/main.cc:80-81, xi_u = w0 * 2^-32,
+ *         xi_v = w1 * 2^-32 (32-bit uniforms; w2, w3 unused);
+ *       bounce b (b = 1, 2, ...) takes block b, whose words w0..w3 carry the first TWO tries of the
+ *         rejection loop of vec3::random_in_unit_sphere (programs/vec3.h:83-95) as 21-bit uniforms
+ *         f in [0, 2^21), coordinate = -1 + 2 * (f * 2^-21) (random_double(-1, 1), programs/random.h:10-14):
+ *           try A: fx = w0 >> 11, fy = w1 >> 11, fz = w2 >> 11;
+ *           try B: fx = (w0 & 0x7ff) << 10 | w3 >> 22, fy = (w1 & 0x7ff) << 10 | (w3 >> 12 & 0x3ff),
+ *                  fz = (w2 & 0x7ff) << 10 | (w3 >> 2 & 0x3ff);
+ *         a try is kept unless len^2 > 1 (vec3.h:90).  If both are rejected (23 % of bounces) the loop
+ *         continues with xorshift128 (Marsaglia 2003: t = x3; x3 = x2; x2 = x1; x1 = x0; t ^= t << 11;
+ *         t ^= t >> 8; x0 = t ^ x1 ^ (x1 >> 19), state (x0..x3) = (w0..w3), x0 = 1 if all are zero),
+ *         three successive outputs per try, f = output >> 11, until a try is kept.
+ *       rt_ray_color: ray q uses pixel id q, sample 0, bounce blocks from 1.
+ *   - thread safety: distinct rt_scene handles may be used from different host threads concurrently (renders
+ *     that share the per-device constant bank are serialised on the device by the library); one handle must
+ *     not be used by two threads at the same time.
  */
 #ifndef RT_B200_H
 #define RT_B200_H
@@ -32,7 +48,7 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 2
+#define RT_ABI_VERSION 3
 
 typedef enum {
     RT_OK = 0,
@@ -53,6 +69,9 @@ typedef struct {
 } rt_camera;
 
 enum { RT_SCAN_FILTERED = 0, RT_SCAN_EXACT = 1, RT_SCAN_BVH = 2, RT_SCAN_AUTO = 3 };
+/* what ray_color adds to p + normal (programs/main.cc:42): vec3::random_in_hemisphere(normal) as the reference
+ * does, or vec3::random_unit_vector() (programs/vec3.h:97-100, shipped but unused: the book's Lambertian) */
+enum { RT_SCATTER_HEMISPHERE = 0, RT_SCATTER_LAMBERTIAN = 1 };
 
 /* The constants main() and ray_color hard-code, as parameters. */
 typedef struct {
@@ -68,6 +87,14 @@ typedef struct {
     int32_t shard_rank;          /* multi-GPU: this call renders tiles t with t % shard_count == shard_rank */
     int32_t shard_count;         /* 1 = whole frame */
     int32_t reserved[3];
+    /* ABI 3: the constants ray_color hard-codes.  custom_shading == 0 (a zero-filled struct)
+     * renders with the reference's values and ignores the four fields below, so the default path stays the
+     * reference bit for bit. */
+    int32_t custom_shading;      /* 1: use scatter_mode / albedo / sky_a / sky_b */
+    int32_t scatter_mode;        /* RT_SCATTER_*; programs/main.cc:42 */
+    double albedo;               /* programs/main.cc:43 returns 0.5 * ray_color(...); 0 <= albedo <= 1 */
+    double sky_a[3], sky_b[3];   /* programs/main.cc:48: (1-t)*sky_a + t*sky_b, reference (1,1,1) and (0.5,0.7,1.0);
+                                    each component in [0, 1] (radiance sums are 20.44 fixed point) */
 } rt_params;
 
 typedef struct {
@@ -94,6 +121,10 @@ typedef struct {
 
 int rt_abi_version(void);
 const char* rt_last_error(void);
+
+/* Fills *params with what programs/main.cc hard-codes (tmin 0, jitter on, albedo 0.5, the sky colours, hemisphere
+ * scatter; custom_shading = 0) plus this library's defaults (seed 0, exact early-out on, RT_SCAN_AUTO, one shard). */
+int rt_params_init(rt_params* params, int32_t width, int32_t height, int32_t spp, int32_t max_depth);
 
 /* Flatten of hittable_list::objects (programs/hittable_list.h:40) with sphere::centre / radius
  * (programs/sphere.h:18-19): centres_xyz = 3n doubles, radii = n doubles, list order.  Uploads to
@@ -154,6 +185,11 @@ int rt_hit(const rt_scene* scene, const double* org, const double* dir, int32_t 
  * blocks from 1.  rgb_out = 3*nrays doubles. */
 int rt_ray_color(const rt_scene* scene, const double* org, const double* dir, int32_t nrays, int32_t depth,
                  uint64_t seed, int32_t early_out, int32_t scan_mode, double* rgb_out, rt_stats* stats_out);
+
+/* The same with tmin, the shading constants, max_depth (= depth), seed, early_out and scan_mode taken from *params
+ * (width / height / spp / shards are not used). */
+int rt_ray_color_params(const rt_scene* scene, const double* org, const double* dir, int32_t nrays,
+                        const rt_params* params, double* rgb_out, rt_stats* stats_out);
 
 /* write_color's arithmetic (programs/color.h:16-23) on device: summed colour + spp -> 3 ints per pixel. */
 int rt_write_color(const double* rgb_sum, int32_t npix, int32_t spp, int32_t device, int32_t* out);

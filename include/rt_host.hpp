@@ -306,10 +306,18 @@ struct frame {
 };
 
 inline rt_params default_params(int width, int height, int spp, int max_depth, uint64_t seed = 0) {
-    rt_params p{};
-    p.width = width; p.height = height; p.spp = spp; p.max_depth = max_depth;
-    p.seed = seed; p.tmin = 0.0;  // programs/main.cc:40
-    p.jitter = 1; p.early_out = 1; p.scan_mode = RT_SCAN_AUTO; p.shard_rank = 0; p.shard_count = 1;
+    rt_params p;
+    check(rt_params_init(&p, width, height, spp, max_depth));  // tmin 0, albedo 0.5, the sky, hemisphere scatter: main.cc:40-48
+    p.seed = seed;
+    return p;
+}
+// The constants ray_color hard-codes (programs/main.cc:40,42,43,48) as arguments, e.g. the book's next chapter:
+//     rt_params p = rt::with_shading(rt::default_params(w, h, spp, depth), 0.001, 0.5, RT_SCATTER_LAMBERTIAN);
+inline rt_params with_shading(rt_params p, double tmin, double albedo, int scatter_mode = RT_SCATTER_HEMISPHERE,
+                              const color& sky_a = color(1.0, 1.0, 1.0), const color& sky_b = color(0.5, 0.7, 1.0)) {
+    p.tmin = tmin;
+    p.custom_shading = 1; p.scatter_mode = scatter_mode; p.albedo = albedo;
+    for (int i = 0; i < 3; ++i) { p.sky_a[i] = sky_a[i]; p.sky_b[i] = sky_b[i]; }
     return p;
 }
 

@@ -78,6 +78,31 @@ inline uint64_t row_seed(uint64_t seed, int j) {
     return seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(j + 1));
 }
 
+/* The constants main.cc:34-49 hard-codes, as arguments (layout == orc_shading of oracle/rt_oracle.h). */
+struct ref_shading {
+    double tmin;
+    double albedo;
+    double sky_a[3], sky_b[3];
+    int scatter_mode;   /* 0: vec3::random_in_hemisphere (main.cc:42); 1: vec3::random_unit_vector (vec3.h:97-100) */
+};
+
+/* ray_color with those arguments, every operation done by the reference's own classes and operators
+ * (hittable::hit, vec3 arithmetic, unit_vector, vec3::random_*), in the shape of main.cc:34-49.  With the
+ * reference's constants it returns what the reference's ray_color returns, bit for bit
+ * (tests/test_oracle_vs_ref.py); it pins the parameterised oracle where main.cc's literals cannot. */
+color ray_color_param(const ray& r, const hittable& world, int depth, const ref_shading& sh) {
+    if (depth < 0) return color(0, 0, 0);
+    hit_record rec;
+    if (world.hit(r, sh.tmin, infinity, rec)) {
+        vec3 bounce = sh.scatter_mode == 1 ? vec3::random_unit_vector() : vec3::random_in_hemisphere(rec.normal);
+        vec3 target = rec.p + rec.normal + bounce;
+        return sh.albedo * ray_color_param(ray(rec.p, target - rec.p), world, depth - 1, sh);
+    }
+    vec3 dir = unit_vector(r.direction());
+    double t = 0.5 * (dir.y() + 1.0);
+    return (1.0 - t) * color(sh.sky_a[0], sh.sky_a[1], sh.sky_a[2]) + t * color(sh.sky_b[0], sh.sky_b[1], sh.sky_b[2]);
+}
+
 }  // namespace
 
 extern "C" {
@@ -218,6 +243,65 @@ void ref_ray_color_batch(const double* centres, const double* radii, int n, cons
         oracle_seed(seeds[q]);
         color c = ray_color(r, world, depth);
         rgb_out[3 * q] = c.x(); rgb_out[3 * q + 1] = c.y(); rgb_out[3 * q + 2] = c.z();
+    }
+}
+
+/* ray_color_param on explicit rays (shading = ref_shading / orc_shading layout). */
+void ref_ray_color_param_batch(const double* centres, const double* radii, int n, const double* org, const double* dir,
+                               const uint64_t* seeds, const void* shading, int nrays, int depth, double* rgb_out) {
+    hittable_list world;
+    build_world(world, centres, radii, n);
+    const ref_shading sh = *static_cast<const ref_shading*>(shading);
+    for (int q = 0; q < nrays; ++q) {
+        ray r(point3(org[3 * q], org[3 * q + 1], org[3 * q + 2]), vec3(dir[3 * q], dir[3 * q + 1], dir[3 * q + 2]));
+        oracle_seed(seeds[q]);
+        color c = ray_color_param(r, world, depth, sh);
+        rgb_out[3 * q] = c.x(); rgb_out[3 * q + 1] = c.y(); rgb_out[3 * q + 2] = c.z();
+    }
+}
+
+/* ref_render_rows with ray_color_param in place of ray_color. */
+void ref_render_rows_param(const double* centres, const double* radii, int n, const double* cam12,
+                           int W, int H, int spp, int max_depth, uint64_t seed, const void* shading, int j0, int j1,
+                           int nthreads, uint8_t* rgb, double* stats) {
+    hittable_list world;
+    build_world(world, centres, radii, n);
+    camera cam;
+    set_camera(cam, cam12);
+    const ref_shading sh = *static_cast<const ref_shading*>(shading);
+    long long tot_casts = 0, tot_black = 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : tot_casts, tot_black)
+#endif
+    for (int j = j1 - 1; j >= j0; --j) {
+        counting_world cw(world);
+        oracle_seed(row_seed(seed, j));
+        long long black = 0;
+        for (int i = 0; i < W; ++i) {
+            color pixel_color(0, 0, 0);
+            for (int s = 0; s < spp; ++s) {
+                double u = ((double)i + random_double()) / (W - 1);
+                double v = ((double)j + random_double()) / (H - 1);
+                color c = ray_color_param(cam.get_ray(u, v), cw, max_depth, sh);
+                if (c.x() == 0 && c.y() == 0 && c.z() == 0) ++black;
+                pixel_color += c;
+            }
+            std::ostringstream os;
+            write_color(os, pixel_color, spp);
+            int r = 0, g = 0, b = 0;
+            std::istringstream is(os.str());
+            is >> r >> g >> b;
+            uint8_t* px = rgb + ((size_t)(H - 1 - j) * W + i) * 3;
+            px[0] = (uint8_t)r; px[1] = (uint8_t)g; px[2] = (uint8_t)b;
+        }
+        tot_casts += cw.casts;
+        tot_black += black;
+    }
+    if (stats) {
+        stats[0] = (double)(j1 - j0) * W * spp;
+        stats[1] = (double)tot_casts;
+        stats[2] = (double)tot_black;
     }
 }
 

@@ -144,6 +144,10 @@ static inline v3 random_in_hemisphere(rng_t* g, v3 normal) {
     return v3_neg(rv);
 }
 
+/* programs/vec3.h:97-100: unit_vector(random_in_unit_sphere()) -- present but unused in the reference's
+ * main.cc; the book's Lambertian scatter (orc_shading.scatter_mode == 1) */
+static inline v3 random_unit_vector(rng_t* g) { return v3_unit(random_in_unit_sphere(g)); }
+
 /* --------------------------------------------------------------- geometry */
 typedef struct { v3 o, d; } ray_t;
 typedef struct { v3 p, normal; double t; int front_face; double C; } rec_t;
@@ -195,36 +199,50 @@ static inline int list_hit(const world_t* w, const ray_t* r, double tmin, double
     return hit_idx;
 }
 
-/* programs/main.cc:34-49 ray_color, recursion unrolled: the result is 0.5^k * sky(dir_k) or 0, and
- * multiplying by 0.5 is exact, so `att` accumulates the same value the recursion returns
- * (checked bit for bit against libref.so).  depth < 0 -> black (main.cc:36), tmin = 0 (main.cc:40).
- * early_out: if the kept hit has t == 0 and C == 0 exactly, the next origin equals this one, every
- * later cast hits that sphere at t == 0 again, and the path must end black: return 0 now. */
-static inline v3 ray_color(ray_t r, const world_t* w, int depth, rng_t* g, int early_out, orc_stats* st,
-                           int* first_hit) {
-    double att = 1.0;
+/* programs/main.cc:34-49 ray_color, recursion unrolled, with the constants the reference hard-codes as
+ * parameters (orc_shading; the defaults are main.cc's: tmin 0 at :40, albedo 0.5 at :43, sky colours at :48,
+ * vec3::random_in_hemisphere at :42).  The recursion returns albedo * (albedo * (... * sky)): one
+ * multiplication per bounce applied to the sky colour from the innermost call outwards, which is what the
+ * loop at the end does (for albedo = 0.5 every product is exact, so this equals the 0.5^k * sky the first
+ * version of this file computed; checked bit for bit against libref.so).  depth < 0 -> black (main.cc:36).
+ * early_out (tmin == 0 only): if the kept hit has t == 0 and C == 0 exactly, the next origin equals this
+ * one, every later cast hits that sphere at t == 0 again, and the path must end black: return 0 now. */
+static inline v3 ray_color(ray_t r, const world_t* w, int depth, rng_t* g, const orc_shading* sh, int early_out,
+                           orc_stats* st, int* first_hit) {
+    int bounces = 0;
     int first = 1;
     for (;;) {
-        if (depth < 0) return v3_make(0, 0, 0);
+        if (depth < 0) return v3_make(0, 0, 0);   /* albedo * ... * 0 == 0 for every finite albedo >= 0 */
         rec_t rec;
         rec.t = 0; rec.C = 1;
         st->casts += 1;
-        int k = list_hit(w, &r, 0, INFINITY, &rec);
+        int k = list_hit(w, &r, sh->tmin, INFINITY, &rec);
         if (first) { *first_hit = k; first = 0; }
         if (k < 0) break;
-        if (early_out && rec.t == 0 && rec.C == 0) { st->early_outs += 1; return v3_make(0, 0, 0); }
-        /* main.cc:42-43: target = (p + normal) + rih; next ray = (p, target - p) */
-        v3 target = v3_add(v3_add(rec.p, rec.normal), random_in_hemisphere(g, rec.normal));
+        if (early_out && sh->tmin == 0 && rec.t == 0 && rec.C == 0) { st->early_outs += 1; return v3_make(0, 0, 0); }
+        /* main.cc:42-43: target = (p + normal) + scatter; next ray = (p, target - p) */
+        v3 sc = sh->scatter_mode == ORC_SCATTER_LAMBERTIAN ? random_unit_vector(g) : random_in_hemisphere(g, rec.normal);
+        v3 target = v3_add(v3_add(rec.p, rec.normal), sc);
         r.o = rec.p;
         r.d = v3_sub(target, rec.p);
-        att = 0.5 * att;
+        ++bounces;
         --depth;
     }
     /* main.cc:46-48 */
     v3 ud = v3_unit(r.d);
     double t = 0.5 * (ud.e[1] + 1.0);
-    v3 sky = v3_add(v3_scale(1.0 - t, v3_make(1.0, 1.0, 1.0)), v3_scale(t, v3_make(0.5, 0.7, 1.0)));
-    return v3_scale(att, sky);
+    v3 c = v3_add(v3_scale(1.0 - t, v3_make(sh->sky_a[0], sh->sky_a[1], sh->sky_a[2])),
+                  v3_scale(t, v3_make(sh->sky_b[0], sh->sky_b[1], sh->sky_b[2])));
+    for (int b = 0; b < bounces; ++b) c = v3_scale(sh->albedo, c);   /* main.cc:43, once per unwound call */
+    return c;
+}
+
+void orc_default_shading(orc_shading* sh) {
+    sh->tmin = 0.0;                                            /* programs/main.cc:40 */
+    sh->albedo = 0.5;                                          /* programs/main.cc:43 */
+    sh->sky_a[0] = 1.0; sh->sky_a[1] = 1.0; sh->sky_a[2] = 1.0;  /* programs/main.cc:48 */
+    sh->sky_b[0] = 0.5; sh->sky_b[1] = 0.7; sh->sky_b[2] = 1.0;
+    sh->scatter_mode = ORC_SCATTER_HEMISPHERE;                 /* programs/main.cc:42 */
 }
 
 /* programs/camera.h:25-28: dir = ((llc + u*horizontal) + v*vertical) - origin */
@@ -282,6 +300,7 @@ long orc_main_ppm(uint64_t seed, char* buf, long cap) {
     const int spp = 100, max_depth = 50;
     rng_t g; memset(&g, 0, sizeof g); g.mode = ORC_RNG_RAND15; g.state = seed;
     orc_stats st; memset(&st, 0, sizeof st);
+    orc_shading sh; orc_default_shading(&sh);
     long len = 0;
     char line[64];
     int m = snprintf(line, sizeof line, "P3\n%d %d\n255\n", W, H);
@@ -295,7 +314,7 @@ long orc_main_ppm(uint64_t seed, char* buf, long cap) {
                 double u = ((double)i + xu) / (W - 1);
                 double v = ((double)j + xv) / (H - 1);
                 int fh;
-                px = v3_add(px, ray_color(get_ray(cam12, u, v), &w, max_depth, &g, 0, &st, &fh));
+                px = v3_add(px, ray_color(get_ray(cam12, u, v), &w, max_depth, &g, &sh, 0, &st, &fh));
             }
             int q[3]; write_color(px, spp, q);
             m = snprintf(line, sizeof line, "%d %d %d\n", q[0], q[1], q[2]);
@@ -305,10 +324,13 @@ long orc_main_ppm(uint64_t seed, char* buf, long cap) {
     return len <= cap ? len : -len;
 }
 
-void orc_render_rows(const double* centres, const double* radii, int n, const double* cam12,
-                     int W, int H, int spp, int max_depth, uint64_t seed, int rng_mode, int early_out,
-                     int j0, int j1, int nthreads, uint8_t* rgb, double* rgb_sum, orc_stats* stats) {
+void orc_render_rows_ex(const double* centres, const double* radii, int n, const double* cam12,
+                        int W, int H, int spp, int max_depth, uint64_t seed, int rng_mode, int early_out,
+                        const orc_shading* shading, int j0, int j1, int nthreads, uint8_t* rgb, double* rgb_sum,
+                        orc_stats* stats) {
     world_t w = {n, centres, radii};
+    orc_shading sh;
+    if (shading) sh = *shading; else orc_default_shading(&sh);
     double t_casts = 0, t_black = 0, t_prim = 0, t_eo = 0;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
@@ -328,7 +350,7 @@ void orc_render_rows(const double* centres, const double* radii, int n, const do
                 double u = ((double)i + xu) / (W - 1);
                 double v = ((double)j + xv) / (H - 1);
                 int fh = -1;
-                v3 c = ray_color(get_ray(cam12, u, v), &w, max_depth, &g, early_out, &st, &fh);
+                v3 c = ray_color(get_ray(cam12, u, v), &w, max_depth, &g, &sh, early_out, &st, &fh);
                 if (c.e[0] == 0 && c.e[1] == 0 && c.e[2] == 0) st.black += 1;
                 if (fh >= 0) st.primary_hits += 1;
                 px = v3_add(px, c);   /* programs/vec3.h:42-48 operator+= */
@@ -346,6 +368,13 @@ void orc_render_rows(const double* centres, const double* radii, int n, const do
         stats->samples = (double)(j1 - j0) * W * spp;
         stats->casts = t_casts; stats->black = t_black; stats->primary_hits = t_prim; stats->early_outs = t_eo;
     }
+}
+
+void orc_render_rows(const double* centres, const double* radii, int n, const double* cam12,
+                     int W, int H, int spp, int max_depth, uint64_t seed, int rng_mode, int early_out,
+                     int j0, int j1, int nthreads, uint8_t* rgb, double* rgb_sum, orc_stats* stats) {
+    orc_render_rows_ex(centres, radii, n, cam12, W, H, spp, max_depth, seed, rng_mode, early_out, NULL, j0, j1, nthreads,
+                       rgb, rgb_sum, stats);
 }
 
 void orc_primary_hits(const double* centres, const double* radii, int n, const double* cam12,
@@ -401,10 +430,12 @@ void orc_sphere_hit_batch(const double* centre, const double* radius, const doub
     }
 }
 
-void orc_ray_color_batch(const double* centres, const double* radii, int n, const double* org, const double* dir,
-                         const uint64_t* seeds, int rng_mode, int early_out, int nrays, int depth, double* rgb_out,
-                         orc_stats* stats) {
+void orc_ray_color_batch_ex(const double* centres, const double* radii, int n, const double* org, const double* dir,
+                            const uint64_t* seeds, int rng_mode, int early_out, const orc_shading* shading, int nrays,
+                            int depth, double* rgb_out, orc_stats* stats) {
     world_t w = {n, centres, radii};
+    orc_shading sh;
+    if (shading) sh = *shading; else orc_default_shading(&sh);
     orc_stats st; memset(&st, 0, sizeof st);
     for (int q = 0; q < nrays; ++q) {
         ray_t r = {v3_make(org[3 * q], org[3 * q + 1], org[3 * q + 2]), v3_make(dir[3 * q], dir[3 * q + 1], dir[3 * q + 2])};
@@ -413,13 +444,19 @@ void orc_ray_color_batch(const double* centres, const double* radii, int n, cons
         if (rng_mode == ORC_RNG_RAND15) g.state = seeds[q];
         else { g.key[0] = (uint32_t)seeds[0]; g.key[1] = (uint32_t)(seeds[0] >> 32); g.pix = (uint32_t)q; g.smp = 0; g.blk = 1; }
         int fh = -1;
-        v3 c = ray_color(r, &w, depth, &g, early_out, &st, &fh);
+        v3 c = ray_color(r, &w, depth, &g, &sh, early_out, &st, &fh);
         st.samples += 1;
         if (c.e[0] == 0 && c.e[1] == 0 && c.e[2] == 0) st.black += 1;
         if (fh >= 0) st.primary_hits += 1;
         memcpy(rgb_out + 3 * (size_t)q, c.e, 24);
     }
     if (stats) *stats = st;
+}
+
+void orc_ray_color_batch(const double* centres, const double* radii, int n, const double* org, const double* dir,
+                         const uint64_t* seeds, int rng_mode, int early_out, int nrays, int depth, double* rgb_out,
+                         orc_stats* stats) {
+    orc_ray_color_batch_ex(centres, radii, n, org, dir, seeds, rng_mode, early_out, NULL, nrays, depth, rgb_out, stats);
 }
 
 void orc_get_ray_batch(const double* cam12, const double* uv, int nq, double* out) {

@@ -36,6 +36,19 @@ typedef struct {
     double early_outs;    /* paths cut by the exact early-out (only if enabled) */
 } orc_stats;
 
+/* The constants programs/main.cc hard-codes in ray_color, as parameters.  orc_default_shading
+ * fills the reference's values: tmin 0 (main.cc:40), albedo 0.5 (main.cc:43), sky (1,1,1) -> (0.5,0.7,1.0)
+ * (main.cc:48), scatter = vec3::random_in_hemisphere (main.cc:42).  ORC_SCATTER_LAMBERTIAN swaps in
+ * vec3::random_unit_vector (programs/vec3.h:97-100, present but unused by the reference's main.cc). */
+enum { ORC_SCATTER_HEMISPHERE = 0, ORC_SCATTER_LAMBERTIAN = 1 };
+typedef struct {
+    double tmin;
+    double albedo;
+    double sky_a[3], sky_b[3];
+    int scatter_mode;
+} orc_shading;
+void orc_default_shading(orc_shading* sh);
+
 /* Philox4x32-10 (Salmon et al., SC'11), one block. */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
@@ -52,6 +65,12 @@ void orc_render_rows(const double* centres, const double* radii, int n, const do
                      int W, int H, int spp, int max_depth, uint64_t seed, int rng_mode, int early_out,
                      int j0, int j1, int nthreads, uint8_t* rgb, double* rgb_sum, orc_stats* stats);
 
+/* the same with explicit shading parameters (NULL = the reference's constants) */
+void orc_render_rows_ex(const double* centres, const double* radii, int n, const double* cam12,
+                        int W, int H, int spp, int max_depth, uint64_t seed, int rng_mode, int early_out,
+                        const orc_shading* shading, int j0, int j1, int nthreads, uint8_t* rgb, double* rgb_sum,
+                        orc_stats* stats);
+
 void orc_primary_hits(const double* centres, const double* radii, int n, const double* cam12,
                       int W, int H, int32_t* idx, double* t);
 
@@ -67,6 +86,10 @@ void orc_sphere_hit_batch(const double* centre, const double* radius, const doub
 void orc_ray_color_batch(const double* centres, const double* radii, int n, const double* org, const double* dir,
                          const uint64_t* seeds, int rng_mode, int early_out, int nrays, int depth, double* rgb_out,
                          orc_stats* stats);
+
+void orc_ray_color_batch_ex(const double* centres, const double* radii, int n, const double* org, const double* dir,
+                            const uint64_t* seeds, int rng_mode, int early_out, const orc_shading* shading, int nrays,
+                            int depth, double* rgb_out, orc_stats* stats);
 
 void orc_get_ray_batch(const double* cam12, const double* uv, int nq, double* out);
 void orc_default_camera(double* cam12, double* aspect);

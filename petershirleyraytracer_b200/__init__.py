@@ -17,6 +17,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(PKG_DIR, "librt_b200.so")  # env override: tuning builds only
 
 SCAN_FILTERED, SCAN_EXACT, SCAN_BVH, SCAN_AUTO = 0, 1, 2, 3
+SCATTER_HEMISPHERE, SCATTER_LAMBERTIAN = 0, 1
+ABI_VERSION = 3
 TILE_W, TILE_H = 8, 8
 
 # every symbol include/rt.h declares (tests check the built library exports all of them)
@@ -25,6 +27,7 @@ ABI_SYMBOLS = [
     "rt_render_device", "rt_render_finish", "rt_get_tile_layout", "rt_deinterleave", "rt_primary_hits", "rt_hit",
     "rt_ray_color", "rt_write_color", "rt_get_ray", "rt_philox", "rt_measure_fp32_peak", "rt_device_info",
     "rt_check_division", "rt_update_scene", "rt_accum_bytes", "rt_render_pass", "rt_render_pass_device",
+    "rt_params_init", "rt_ray_color_params",
 ]
 
 
@@ -37,7 +40,9 @@ class RtParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("max_depth", C.c_int32),
                 ("seed", C.c_uint64), ("tmin", C.c_double), ("jitter", C.c_int32), ("early_out", C.c_int32),
                 ("scan_mode", C.c_int32), ("shard_rank", C.c_int32), ("shard_count", C.c_int32),
-                ("reserved", C.c_int32 * 3)]
+                ("reserved", C.c_int32 * 3),
+                ("custom_shading", C.c_int32), ("scatter_mode", C.c_int32), ("albedo", C.c_double),
+                ("sky_a", C.c_double * 3), ("sky_b", C.c_double * 3)]
 
 
 class RtStats(C.Structure):
@@ -98,6 +103,10 @@ def lib() -> C.CDLL:
     L.rt_render_pass_device.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtParams), C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_void_p]
     L.rt_check_division.argtypes = [C.c_int32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.rt_params_init.argtypes = [C.POINTER(RtParams), C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    L.rt_ray_color_params.argtypes = [vp, dp, dp, C.c_int32, C.POINTER(RtParams), dp, C.POINTER(RtStats)]
+    if L.rt_abi_version() != ABI_VERSION:
+        raise RtError(f"{LIB_PATH} has ABI {L.rt_abi_version()}, this binding needs {ABI_VERSION}: rebuild the library")
     _lib = L
     return L
 
@@ -167,9 +176,22 @@ class Camera:
 
 def make_params(width: int, height: int, spp: int, max_depth: int = 50, seed: int = 0, tmin: float = 0.0,
                 jitter: bool = True, early_out: bool = True, scan_mode: int = SCAN_AUTO, shard_rank: int = 0,
-                shard_count: int = 1, paths_per_lane: int = 0, chunks: int = 0, cull_smem: bool = False) -> RtParams:
+                shard_count: int = 1, paths_per_lane: int = 0, chunks: int = 0, cull_smem: bool = False,
+                albedo: float | None = None, sky_a=None, sky_b=None, scatter_mode: int | None = None) -> RtParams:
+    """rt_params.  albedo / sky_a / sky_b / scatter_mode (any of them given) switch custom_shading on; left alone, the
+    render uses the reference's constants (programs/main.cc:42,43,48)."""
     p = RtParams()
-    p.width, p.height, p.spp, p.max_depth = width, height, spp, max_depth
+    _check(lib().rt_params_init(C.byref(p), width, height, spp, max_depth))
+    if albedo is not None or sky_a is not None or sky_b is not None or scatter_mode is not None:
+        p.custom_shading = 1
+        if albedo is not None:
+            p.albedo = albedo
+        if sky_a is not None:
+            p.sky_a[:] = [float(x) for x in sky_a]
+        if sky_b is not None:
+            p.sky_b[:] = [float(x) for x in sky_b]
+        if scatter_mode is not None:
+            p.scatter_mode = scatter_mode
     p.seed, p.tmin = seed & 0xFFFFFFFFFFFFFFFF, tmin
     p.jitter, p.early_out, p.scan_mode = int(jitter), int(early_out), scan_mode
     p.shard_rank, p.shard_count = shard_rank, shard_count
@@ -318,6 +340,16 @@ def ray_color(scene: Scene, org, dirs, depth: int, seed: int = 0, early_out: boo
     st = RtStats()
     _check(lib().rt_ray_color(scene.handle, _dptr(org), _dptr(dirs), n, depth, seed & 0xFFFFFFFFFFFFFFFF, int(early_out),
                               scan_mode, _dptr(rgb), C.byref(st)))
+    return rgb, st.as_dict()
+
+
+def ray_color_params(scene: Scene, org, dirs, params: RtParams):
+    """rt_ray_color_params: ray_color with tmin / shading / depth / seed / early_out / scan_mode from `params`."""
+    org, dirs = _f64(org).reshape(-1, 3), _f64(dirs).reshape(-1, 3)
+    n = len(org)
+    rgb = np.empty((n, 3), dtype=np.float64)
+    st = RtStats()
+    _check(lib().rt_ray_color_params(scene.handle, _dptr(org), _dptr(dirs), n, C.byref(params), _dptr(rgb), C.byref(st)))
     return rgb, st.as_dict()
 
 

@@ -100,7 +100,26 @@ int check_params(const rt_params* p) {
     if (p->shard_count < 1 || p->shard_rank < 0 || p->shard_rank >= p->shard_count)
         return fail(RT_ERR_INVALID, "bad shard_rank / shard_count");
     if (p->scan_mode < 0 || p->scan_mode > RT_SCAN_AUTO) return fail(RT_ERR_INVALID, "bad scan_mode");
+    if (p->custom_shading) {
+        if (p->scatter_mode != RT_SCATTER_HEMISPHERE && p->scatter_mode != RT_SCATTER_LAMBERTIAN)
+            return fail(RT_ERR_INVALID, "bad scatter_mode");
+        if (!(p->albedo >= 0.0 && p->albedo <= 1.0)) return fail(RT_ERR_INVALID, "albedo must be in [0, 1]");
+        for (int c = 0; c < 3; ++c)
+            if (!(p->sky_a[c] >= 0.0 && p->sky_a[c] <= 1.0) || !(p->sky_b[c] >= 0.0 && p->sky_b[c] <= 1.0))
+                return fail(RT_ERR_INVALID, "sky colour components must be in [0, 1] (radiance sums are 20.44 fixed point)");
+    }
     return RT_OK;
+}
+
+rt::ShadeDev shade_dev(const rt_params* p) {
+    rt::ShadeDev sh;
+    std::memset(&sh, 0, sizeof sh);
+    sh.custom = p->custom_shading ? 1 : 0;
+    sh.albedo = sh.custom ? p->albedo : 0.5;                                       // programs/main.cc:43
+    const double a[3] = {1.0, 1.0, 1.0}, b[3] = {0.5, 0.7, 1.0};                   // programs/main.cc:48
+    for (int c = 0; c < 3; ++c) { sh.sky_a[c] = sh.custom ? p->sky_a[c] : a[c]; sh.sky_b[c] = sh.custom ? p->sky_b[c] : b[c]; }
+    sh.lambertian = (sh.custom && p->scatter_mode == RT_SCATTER_LAMBERTIAN) ? 1 : 0;
+    return sh;
 }
 
 void tile_layout(const rt_params* p, rt_tile_layout* L) {
@@ -160,6 +179,7 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
         a.cam_hor[c] = cam->horizontal[c]; a.cam_ver[c] = cam->vertical[c];
     }
     a.tmin = p->tmin;
+    a.sh = shade_dev(p);
     a.W = p->width; a.H = p->height; a.spp = p->spp; a.max_depth = p->max_depth;
     a.key0 = (uint32_t)p->seed; a.key1 = (uint32_t)(p->seed >> 32);
     a.jitter = p->jitter; a.scan_mode = mode;
@@ -179,8 +199,12 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     // cull array source: constant bank (default; FFMAs then read a uniform-register operand) or the
     // TMA-staged shared-memory copy (reserved[2] == 1), kept for A/B evidence
     const bool use_const = p->reserved[2] != 1 && mode == RT_SCAN_FILTERED;
+    // One critical section from the wait on the previous constant-bank render through this render's launch and
+    // event record: a second host thread rendering another FILTERED scene on another stream of this device then
+    // queues its copy into the bank strictly behind this kernel (and not between this copy and this launch).
+    std::unique_lock<std::mutex> bank_lock;
     if (use_const) {
-        std::lock_guard<std::mutex> lock(g_const_bank.mu);
+        bank_lock = std::unique_lock<std::mutex>(g_const_bank.mu);
         cudaEvent_t& prev = g_const_bank.last[sc->device & 63];
         if (prev) RT_CUDA(cudaStreamWaitEvent(stream, prev, 0));
         RT_CUDA(cudaMemcpyToSymbolAsync(rt::c_filt, sc->d_filt, (size_t)(sc->npad + rt::kScanPad) * sizeof(float4), 0,
@@ -230,10 +254,10 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     RT_CUDA(cudaGetLastError());
     RT_CUDA(cudaEventRecord(sc->ev1, stream));
     if (use_const) {
-        std::lock_guard<std::mutex> lock(g_const_bank.mu);
         cudaEvent_t& prev = g_const_bank.last[sc->device & 63];
         if (!prev) RT_CUDA(cudaEventCreateWithFlags(&prev, cudaEventDisableTiming));
         RT_CUDA(cudaEventRecord(prev, stream));
+        bank_lock.unlock();
     }
     sc->pending = true; sc->last_stream = stream; sc->last_mode = mode; sc->last_launches = 1;
     return RT_OK;
@@ -331,6 +355,19 @@ extern "C" {
 
 int rt_abi_version(void) { return RT_ABI_VERSION; }
 const char* rt_last_error(void) { return g_err.c_str(); }
+
+int rt_params_init(rt_params* p, int32_t width, int32_t height, int32_t spp, int32_t max_depth) {
+    if (!p) return fail(RT_ERR_INVALID, "params is NULL");
+    std::memset(p, 0, sizeof *p);
+    p->width = width; p->height = height; p->spp = spp; p->max_depth = max_depth;
+    p->seed = 0; p->tmin = 0.0;                      // programs/main.cc:40
+    p->jitter = 1; p->early_out = 1; p->scan_mode = RT_SCAN_AUTO; p->shard_rank = 0; p->shard_count = 1;
+    p->custom_shading = 0; p->scatter_mode = RT_SCATTER_HEMISPHERE;   // programs/main.cc:42
+    p->albedo = 0.5;                                 // programs/main.cc:43
+    p->sky_a[0] = p->sky_a[1] = p->sky_a[2] = 1.0;   // programs/main.cc:48
+    p->sky_b[0] = 0.5; p->sky_b[1] = 0.7; p->sky_b[2] = 1.0;
+    return RT_OK;
+}
 
 int rt_device_info(int32_t device, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, char* name, int32_t name_cap) {
     cudaDeviceProp prop;
@@ -583,9 +620,11 @@ int rt_hit(const rt_scene* scene, const double* org, const double* dir, int32_t 
     return RT_OK;
 }
 
-int rt_ray_color(const rt_scene* scene, const double* org, const double* dir, int32_t nrays, int32_t depth, uint64_t seed,
-                 int32_t early_out, int32_t scan_mode, double* rgb_out, rt_stats* st) {
+static int ray_color_impl(const rt_scene* scene, const double* org, const double* dir, int32_t nrays, int32_t depth,
+                          uint64_t seed, int32_t early_out, int32_t scan_mode, double tmin, const rt::ShadeDev& sh,
+                          double* rgb_out, rt_stats* st) {
     if (!scene || !org || !dir || !rgb_out || nrays < 0) return fail(RT_ERR_INVALID, "bad argument");
+    if (depth > 1000) return fail(RT_ERR_INVALID, "depth must be <= 1000 (as rt_params.max_depth)");
     if (st) std::memset(st, 0, sizeof *st);
     if (nrays == 0) return RT_OK;
     rt_scene* sc = const_cast<rt_scene*>(scene);
@@ -602,7 +641,9 @@ int rt_ray_color(const rt_scene* scene, const double* org, const double* dir, in
     rt::RayBatchArgs a;
     std::memset(&a, 0, sizeof a);
     a.sc = scene_dev(sc, mode); a.org = d_org.p; a.dir = d_dir.p; a.nrays = nrays; a.scan_mode = mode;
-    a.depth = depth; a.early_out = early_out; a.key0 = (uint32_t)seed; a.key1 = (uint32_t)(seed >> 32);
+    a.tmin = tmin; a.sh = sh;
+    a.depth = depth; a.early_out = (early_out && tmin == 0.0) ? 1 : 0;  // the cut is only exact for tmin == 0
+    a.key0 = (uint32_t)seed; a.key1 = (uint32_t)(seed >> 32);
     a.rgb_out = d_rgb.p; a.stats = sc->d_stats;
     const rt::BatchSmem S = rt::batch_smem(a.sc.npad);
     RT_CUDA(cudaFuncSetAttribute(rt::ray_color_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
@@ -619,6 +660,24 @@ int rt_ray_color(const rt_scene* scene, const double* org, const double* dir, in
         st->overflows = h[rt::ST_OVERFLOWS]; st->launches = 1;
     }
     return RT_OK;
+}
+
+int rt_ray_color(const rt_scene* scene, const double* org, const double* dir, int32_t nrays, int32_t depth, uint64_t seed,
+                 int32_t early_out, int32_t scan_mode, double* rgb_out, rt_stats* st) {
+    rt_params p;
+    rt_params_init(&p, 2, 2, 1, depth);
+    return ray_color_impl(scene, org, dir, nrays, depth, seed, early_out, scan_mode, 0.0, shade_dev(&p), rgb_out, st);
+}
+
+int rt_ray_color_params(const rt_scene* scene, const double* org, const double* dir, int32_t nrays, const rt_params* p,
+                        double* rgb_out, rt_stats* st) {
+    if (!p) return fail(RT_ERR_INVALID, "params is NULL");
+    rt_params q = *p;
+    q.width = q.height = 2; q.spp = 1; q.shard_rank = 0; q.shard_count = 1;   // not used here: keep check_params quiet
+    int rc = check_params(&q);
+    if (rc) return rc;
+    return ray_color_impl(scene, org, dir, nrays, p->max_depth, p->seed, p->early_out, p->scan_mode, p->tmin, shade_dev(p),
+                          rgb_out, st);
 }
 
 int rt_write_color(const double* rgb_sum, int32_t npix, int32_t spp, int32_t device, int32_t* out) {

@@ -4,7 +4,7 @@
 // EXACTLY: every quantity that feeds a decision or the image is computed in FP64 with one rounding per
 // operation in the reference's evaluation order (__dmul_rn/__dadd_rn/... never contract into FMA).
 // What makes it fast is that the O(N) part of hittable_list::hit (programs/hittable_list.cc:9-17) is a
-// *conservative FP32 cull*: 8 FP32-pipe instructions per (ray, sphere) decide "cannot be hit" with a
+// *conservative FP32 cull*: 7 FP32-pipe instructions per (ray, sphere) decide "cannot be hit" with a
 // rigorous error bound; only the few survivors run the FP64 sphere::hit (programs/sphere.cc:3-40), in
 // list order with the shrinking tmax, so index / t / p / normal are bit-identical to the reference.
 #pragma once
@@ -111,8 +111,18 @@ struct SceneDev {
     const int32_t* bvh_leaf;   // sphere list indices, leaf by leaf
 };
 
+// The constants programs/main.cc hard-codes in ray_color, as launch arguments (rt_params).
+// custom == 0 selects the reference's own values through the original code path (exact 0.5^k attenuation).
+struct ShadeDev {
+    double albedo;             // programs/main.cc:43
+    double sky_a[3], sky_b[3]; // programs/main.cc:48: (1-t)*sky_a + t*sky_b
+    int custom;                // 0: albedo 0.5, sky (1,1,1) -> (0.5,0.7,1.0), the fields above are not read
+    int lambertian;            // 0: vec3::random_in_hemisphere (main.cc:42); 1: vec3::random_unit_vector (vec3.h:97-100)
+};
+
 struct RenderArgs {
     SceneDev sc;
+    ShadeDev sh;
     double cam_org[3], cam_llc[3], cam_hor[3], cam_ver[3];
     double tmin;
     int W, H, spp, max_depth;
@@ -171,7 +181,8 @@ __device__ __forceinline__ void stage_bulk(void* s_dst, const void* g_src, uint3
 // B200 (tools/microbench.cu): FFMA with three distinct vector-register sources sustains 22.8 T FMA/s,
 // with a uniform/constant operand 36.2 T FMA/s; the scan costs 11.8 issue slots per test from the
 // constant bank against 13.7 from shared memory (LDS.128 + three-register FFMAs).  The shared-memory
-// variant (TMA-staged) is kept selectable for comparison and for scenes beyond the 64 KB bank.
+// variant (TMA-staged) is kept selectable for comparison (rt_params.reserved[2]); it is the only linear scan
+// for scenes beyond the 64 KB constant bank (up to kMaxLinearSmem entries).
 __constant__ float4 c_filt[kMaxLinear + kScanPad];
 
 struct CullRay {  // per-cast constants, 8 registers
@@ -407,20 +418,38 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
     const float opx = __fadd_ru(fx, padx), opy = __fadd_ru(fy, pady), opz = __fadd_ru(fz, padz);
     const float omx = __fadd_rd(fx, -padx), omy = __fadd_rd(fy, -pady), omz = __fadd_rd(fz, -padz);
     // 1/d in FP32 (__frcp_rn of the rounded component): 2^-23 relative instead of the 2^-24 of rounding the FP64
-    // quotient -- the products below then carry 4 x 2^-24, inside the 1 +- 2^-19 slack -- and no FP64 division;
-    // +-0 and components beyond the float range give +-inf / +-0 exactly as the rounded FP64 quotient would
-    const float ivx = __frcp_rn((float)dx), ivy = __frcp_rn((float)dy), ivz = __frcp_rn((float)dz);
+    // quotient -- the products below then carry 4 x 2^-24, inside the 1 +- 2^-19 slack -- and no FP64 division
+    // A component that is exactly 0 makes the ray parallel to that slab pair: the axis then constrains no distance,
+    // it only decides (below, per box) whether the origin's padded interval overlaps the slab at all.  With iv = 0
+    // and constants -inf / +inf both plane distances come out as -inf / +inf without any inf * 0.  (iv = inf would
+    // give fma(plane, inf, -+inf) = NaN for the plane on the far side of the origin, which fmaxf drops: a false
+    // miss.)  A non-zero component whose FP32 value is zero or denormal (|d| < 2^-126) is not static -- the ray does
+    // cross that slab at some huge t -- and no FP32 reciprocal can bound 1/d: such rays take the sequential scan.
+    const bool zx = dx == 0.0, zy = dy == 0.0, zz = dz == 0.0;
+    const bool zany = zx || zy || zz;
+    {
+        const float kMinNormal = 1.17549435e-38f;
+        if ((!zx && fabsf((float)dx) < kMinNormal) || (!zy && fabsf((float)dy) < kMinNormal) ||
+            (!zz && fabsf((float)dz) < kMinNormal)) {
+            overflow = true;
+            return best;
+        }
+    }
+    const float ivx = zx ? 0.f : __frcp_rn((float)dx), ivy = zy ? 0.f : __frcp_rn((float)dy),
+                ivz = zz ? 0.f : __frcp_rn((float)dz);
     // Slab distances as ONE FFMA per plane: (plane - o) * iv = fma(plane, iv, -(o * iv)).  The constant -(o*iv) is
     // formed exactly in FP64 (24 x 24 bits) and rounded in the direction that keeps the plane's role conservative:
     // for iv > 0 the lo planes give the near distance (must not be overestimated: round down) and the hi planes the
     // far distance (round up); for iv < 0 the roles swap.  The FFMA's own rounding is relative to its result and is
-    // covered by the 1 +- 2^-19 factors like before.  An axis with iv = +-inf yields inf - inf = NaN for both planes,
-    // which fminf/fmaxf drop: that axis then does not constrain the interval (conservative).
+    // covered by the 1 +- 2^-19 factors like before.  (iv is never +-inf here: zero components are static axes,
+    // FP32-denormal ones left above.  iv = +-0 -- a component beyond the float range -- gives both planes the
+    // distance 0, which only asks that the origin lie inside the other two slabs: conservative.)
     const double pxl = -((double)opx * (double)ivx), pyl = -((double)opy * (double)ivy), pzl = -((double)opz * (double)ivz);
     const double pxh = -((double)omx * (double)ivx), pyh = -((double)omy * (double)ivy), pzh = -((double)omz * (double)ivz);
-    const float clx = ivx > 0.f ? __double2float_rd(pxl) : __double2float_ru(pxl), chx = ivx > 0.f ? __double2float_ru(pxh) : __double2float_rd(pxh);
-    const float cly = ivy > 0.f ? __double2float_rd(pyl) : __double2float_ru(pyl), chy = ivy > 0.f ? __double2float_ru(pyh) : __double2float_rd(pyh);
-    const float clz = ivz > 0.f ? __double2float_rd(pzl) : __double2float_ru(pzl), chz = ivz > 0.f ? __double2float_ru(pzh) : __double2float_rd(pzh);
+    const float kFInf = __int_as_float(0x7f800000);
+    const float clx = zx ? -kFInf : (ivx > 0.f ? __double2float_rd(pxl) : __double2float_ru(pxl)), chx = zx ? kFInf : (ivx > 0.f ? __double2float_ru(pxh) : __double2float_rd(pxh));
+    const float cly = zy ? -kFInf : (ivy > 0.f ? __double2float_rd(pyl) : __double2float_ru(pyl)), chy = zy ? kFInf : (ivy > 0.f ? __double2float_ru(pyh) : __double2float_rd(pyh));
+    const float clz = zz ? -kFInf : (ivz > 0.f ? __double2float_rd(pzl) : __double2float_ru(pzl)), chz = zz ? kFInf : (ivz > 0.f ? __double2float_ru(pzh) : __double2float_rd(pzh));
     // the pruning bound: entry distance tn may matter iff tn * (1 - 2^-19) <= RU(best t); kept pre-divided (rounded
     // up, so the test only gets looser) so that a box costs one compare against it
     const float kInvDn = 1.0f + 3.814697265625e-06f;  // > 1 / (1 - 2^-19)
@@ -459,6 +488,14 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
             tn[i] = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
             const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
             hit[i] = tn[i] <= tf * kUp && tn[i] <= bu;   // (empty slots carry NaN boxes: tf = NaN, never hit)
+        }
+        if (zany) {  // static axes: the (padded) origin coordinate must lie inside the slab
+#pragma unroll
+            for (int i = 0; i < W; ++i) {
+                if (zx) hit[i] = hit[i] && lx[i] <= opx && hx[i] >= omx;
+                if (zy) hit[i] = hit[i] && ly[i] <= opy && hy[i] >= omy;
+                if (zz) hit[i] = hit[i] && lz[i] <= opz && hz[i] >= omz;
+            }
         }
         // hit leaves are resolved on the spot (each re-checked against the best found so far)
 #pragma unroll
@@ -554,9 +591,11 @@ __device__ __forceinline__ double cube_coord(uint32_t f) {  // -1 + 2 * (f * 2^-
 // reject both (a try is kept with probability pi/6) continue with xorshift128 (Marsaglia 2003) seeded by the
 // block's four words, three outputs per try (top 21 bits each): a cheap continuation instead of further
 // 10-round blocks, since the warp runs as many loop iterations as its unluckiest lane.
-__device__ __forceinline__ void random_in_hemisphere(uint32_t pix, uint32_t smp, uint32_t& blk, uint32_t k0, uint32_t k1,
-                                                     double nx, double ny, double nz, double& rx, double& ry,
-                                                     double& rz) {
+// lambertian != 0 replaces the hemisphere flip of vec3.h:102-109 by vec3::random_unit_vector (vec3.h:97-100):
+// unit_vector(v) = (1 / v.length()) * v (vec3.h:172-175, 151-154), same rejection tries.
+__device__ __forceinline__ void random_scatter(uint32_t pix, uint32_t smp, uint32_t& blk, uint32_t k0, uint32_t k1,
+                                               double nx, double ny, double nz, int lambertian, double& rx, double& ry,
+                                               double& rz) {
     const uint4 w = philox4x32_10(pix, smp, blk, 0u, k0, k1);
     ++blk;
     uint32_t fx = w.x >> 11, fy = w.y >> 11, fz = w.z >> 11;
@@ -587,21 +626,34 @@ __device__ __forceinline__ void random_in_hemisphere(uint32_t pix, uint32_t smp,
         } while (!ok);
     }
     rx = cube_coord(fx); ry = cube_coord(fy); rz = cube_coord(fz);
-    if (!(ddot(rx, ry, rz, nx, ny, nz) > 0)) { rx = -rx; ry = -ry; rz = -rz; }  // programs/vec3.h:105-108
+    if (lambertian) {
+        const double inv_len = ddiv(1.0, dsqrt(ddot(rx, ry, rz, rx, ry, rz)));   // programs/vec3.h:172-175
+        rx = dmul(inv_len, rx); ry = dmul(inv_len, ry); rz = dmul(inv_len, rz);
+    } else if (!(ddot(rx, ry, rz, nx, ny, nz) > 0)) { rx = -rx; ry = -ry; rz = -rz; }  // programs/vec3.h:105-108
 }
 
-// programs/main.cc:46-48 sky colour of a ray that missed, times att = 0.5^bounces
-__device__ __forceinline__ void sky_color(double dx, double dy, double dz, double A, int bounces, double& r, double& g,
+// programs/main.cc:46-48 sky colour of a ray that missed, times the attenuation of its `bounces` hits.  The
+// recursion returns albedo * (albedo * (... * sky)) (main.cc:43): with the reference's albedo 0.5 every product
+// is exact and equals 0.5^bounces * sky (no denormals: bounces <= 1001 and the reference's sky is >= 0.5); with
+// custom shading the multiplications are applied one by one, innermost first, as the recursion unwinds.
+__device__ __forceinline__ void sky_color(const ShadeDev& sh, double dy, double A, int bounces, double& r, double& g,
                                           double& b) {
     const double inv_len = ddiv(1.0, dsqrt(A));  // unit_vector = v / v.length() = (1/len) * v
     const double uy = dmul(inv_len, dy);
     const double t = dmul(0.5, dadd(uy, 1.0));
     const double omt = dsub(1.0, t);
-    const double att = __longlong_as_double((long long)(1023 - bounces) << 52);  // 0.5^bounces, exact
-    r = dmul(att, dadd(dmul(omt, 1.0), dmul(t, 0.5)));
-    g = dmul(att, dadd(dmul(omt, 1.0), dmul(t, 0.7)));
-    b = dmul(att, dadd(dmul(omt, 1.0), dmul(t, 1.0)));
-    (void)dx; (void)dz;
+    if (!sh.custom) {
+        const double att = __longlong_as_double((long long)(1023 - bounces) << 52);  // 0.5^bounces, exact
+        r = dmul(att, dadd(dmul(omt, 1.0), dmul(t, 0.5)));
+        g = dmul(att, dadd(dmul(omt, 1.0), dmul(t, 0.7)));
+        b = dmul(att, dadd(dmul(omt, 1.0), dmul(t, 1.0)));
+    } else {
+        r = dadd(dmul(omt, sh.sky_a[0]), dmul(t, sh.sky_b[0]));
+        g = dadd(dmul(omt, sh.sky_a[1]), dmul(t, sh.sky_b[1]));
+        b = dadd(dmul(omt, sh.sky_a[2]), dmul(t, sh.sky_b[2]));
+#pragma unroll 1
+        for (int k = 0; k < bounces; ++k) { r = dmul(sh.albedo, r); g = dmul(sh.albedo, g); b = dmul(sh.albedo, b); }
+    }
 }
 
 // programs/color.h:16-23 for one channel

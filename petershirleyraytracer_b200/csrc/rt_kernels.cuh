@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R>::kMinBlocks) render_
                 if (best.k < 0) {
                     // miss: sky (programs/main.cc:46-48) * 0.5^bounces -> fixed-point accumulate
                     double cr, cg, cb;
-                    sky_color(dx, dy, dz, A, bounces, cr, cg, cb);
+                    sky_color(a.sh, dy, A, bounces, cr, cg, cb);
                     const double fs = (double)(1ull << kFixShift);
                     unsigned long long* ap = acc + ((lp >> 6) * kTilePix + (lp & 63)) * 3;
                     atomicAdd(ap + 0, __double2ull_rz(cr * fs));
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R>::kMinBlocks) render_
                     } else {
                         const Record rec = make_record(a.sc, best, ox, oy, oz, dx, dy, dz);
                         double rx, ry, rz;
-                        random_in_hemisphere(m.x, m.y, m.z, a.key0, a.key1, rec.nx, rec.ny, rec.nz, rx, ry, rz);
+                        random_scatter(m.x, m.y, m.z, a.key0, a.key1, rec.nx, rec.ny, rec.nz, a.sh.lambertian, rx, ry, rz);
                         // programs/main.cc:42-43: target = (p + normal) + rv; next ray = (p, target - p)
                         const double tgx = dadd(dadd(rec.px, rec.nx), rx);
                         const double tgy = dadd(dadd(rec.py, rec.ny), ry);
@@ -386,6 +386,7 @@ struct RayBatchArgs {
     double cam_org[3], cam_llc[3], cam_hor[3], cam_ver[3];
     int W, H;
     // ray_color_kernel
+    ShadeDev sh;
     int depth, early_out;
     uint32_t key0, key1;
     // outputs
@@ -503,16 +504,16 @@ __global__ void __launch_bounds__(kThreads) ray_color_kernel(const __grid_consta
         }
         while (__any_sync(0xffffffffu, alive)) {
             const double A = ddot(dx, dy, dz, dx, dy, dz);
-            const Best best = cast_one(a.sc, s_filt, cand, a.scan_mode, alive, ox, oy, oz, dx, dy, dz, A, 0.0,
+            const Best best = cast_one(a.sc, s_filt, cand, a.scan_mode, alive, ox, oy, oz, dx, dy, dz, A, a.tmin,
                                        __longlong_as_double(0x7ff0000000000000ll), n_exact, n_ovf);
             if (!alive) continue;
             ++n_casts;
-            if (best.k < 0) { sky_color(dx, dy, dz, A, bounces, cr, cg, cb); alive = false; continue; }
+            if (best.k < 0) { sky_color(a.sh, dy, A, bounces, cr, cg, cb); alive = false; continue; }
             if (bounces == 0) ++n_primary;
             if (a.early_out && best.t == 0.0 && best.C == 0.0) { ++n_early; ++n_black; alive = false; continue; }
             const Record rec = make_record(a.sc, best, ox, oy, oz, dx, dy, dz);
             double rx, ry, rz;
-            random_in_hemisphere((uint32_t)q, 0u, blk, a.key0, a.key1, rec.nx, rec.ny, rec.nz, rx, ry, rz);
+            random_scatter((uint32_t)q, 0u, blk, a.key0, a.key1, rec.nx, rec.ny, rec.nz, a.sh.lambertian, rx, ry, rz);
             const double tgx = dadd(dadd(rec.px, rec.nx), rx);
             const double tgy = dadd(dadd(rec.py, rec.ny), ry);
             const double tgz = dadd(dadd(rec.pz, rec.nz), rz);

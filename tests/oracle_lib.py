@@ -29,6 +29,23 @@ class OrcStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class OrcShading(C.Structure):
+    """orc_shading / ref_shading: the constants ray_color hard-codes (programs/main.cc:40,42,43,48)."""
+    _fields_ = [("tmin", C.c_double), ("albedo", C.c_double), ("sky_a", C.c_double * 3), ("sky_b", C.c_double * 3),
+                ("scatter_mode", C.c_int)]
+
+
+SCATTER_HEMISPHERE, SCATTER_LAMBERTIAN = 0, 1
+
+
+def shading(tmin=0.0, albedo=0.5, sky_a=(1.0, 1.0, 1.0), sky_b=(0.5, 0.7, 1.0), scatter_mode=SCATTER_HEMISPHERE) -> OrcShading:
+    sh = OrcShading()
+    sh.tmin, sh.albedo, sh.scatter_mode = tmin, albedo, scatter_mode
+    sh.sky_a[:] = list(sky_a)
+    sh.sky_b[:] = list(sky_b)
+    return sh
+
+
 _cache = {}
 
 
@@ -46,6 +63,10 @@ def oracle() -> C.CDLL:
         L.orc_main_ppm.argtypes = [C.c_uint64, C.c_char_p, C.c_long]
         L.orc_render_rows.argtypes = [dp, dp, C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_int, u8p, dp, C.POINTER(OrcStats)]
+        L.orc_render_rows_ex.argtypes = [dp, dp, C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int,
+                                         C.POINTER(OrcShading), C.c_int, C.c_int, C.c_int, u8p, dp, C.POINTER(OrcStats)]
+        L.orc_ray_color_batch_ex.argtypes = [dp, dp, C.c_int, dp, dp, u64p, C.c_int, C.c_int, C.POINTER(OrcShading), C.c_int,
+                                             C.c_int, dp, C.POINTER(OrcStats)]
         L.orc_primary_hits.argtypes = [dp, dp, C.c_int, dp, C.c_int, C.c_int, ip, dp]
         L.orc_hit_batch.argtypes = [dp, dp, C.c_int, dp, dp, C.c_int, C.c_double, C.c_double, ip, dp]
         L.orc_sphere_hit_batch.argtypes = [dp, dp, dp, dp, C.c_int, C.c_double, C.c_double, ip, dp]
@@ -72,6 +93,9 @@ def ref() -> C.CDLL:
         L.ref_hit_batch.argtypes = [dp, dp, C.c_int, dp, dp, C.c_int, C.c_double, C.c_double, ip, dp]
         L.ref_sphere_hit_batch.argtypes = [dp, dp, dp, dp, C.c_int, C.c_double, C.c_double, ip, dp]
         L.ref_ray_color_batch.argtypes = [dp, dp, C.c_int, dp, dp, u64p, C.c_int, C.c_int, dp]
+        L.ref_ray_color_param_batch.argtypes = [dp, dp, C.c_int, dp, dp, u64p, C.POINTER(OrcShading), C.c_int, C.c_int, dp]
+        L.ref_render_rows_param.argtypes = [dp, dp, C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64,
+                                            C.POINTER(OrcShading), C.c_int, C.c_int, C.c_int, u8p, dp]
         L.ref_get_ray_batch.argtypes = [dp, dp, C.c_int, dp]
         L.ref_default_camera.argtypes = [dp, dp]
         L.ref_write_color_batch.argtypes = [dp, C.c_int, C.c_int, ip]
@@ -98,20 +122,24 @@ def main_ppm(which: str, seed: int = 0x9E3779B97F4A7C15) -> bytes:
 
 
 def render(which: str, centres, radii, cam12, W, H, spp, max_depth=50, seed=0, rng_mode=RNG_RAND15, early_out=False,
-           j0=0, j1=None, nthreads=0, want_sums=False):
-    """Returns (rgb (H,W,3) uint8, sums or None, stats dict)."""
+           j0=0, j1=None, nthreads=0, want_sums=False, shading: OrcShading | None = None):
+    """Returns (rgb (H,W,3) uint8, sums or None, stats dict).  shading=None: the reference's constants."""
     centres, radii, cam12 = _f64(centres).reshape(-1, 3), _f64(radii), _f64(cam12)
     j1 = H if j1 is None else j1
     rgb = np.zeros((H, W, 3), dtype=np.uint8)
     if which == "orc":
         sums = np.zeros((H, W, 3), dtype=np.float64) if want_sums else None
         st = OrcStats()
-        oracle().orc_render_rows(_p(centres), _p(radii), len(radii), _p(cam12), W, H, spp, max_depth, seed, rng_mode,
-                                 int(early_out), j0, j1, nthreads, rgb.ctypes.data_as(u8p),
-                                 _p(sums) if want_sums else None, C.byref(st))
+        oracle().orc_render_rows_ex(_p(centres), _p(radii), len(radii), _p(cam12), W, H, spp, max_depth, seed, rng_mode,
+                                    int(early_out), C.byref(shading) if shading is not None else None, j0, j1, nthreads,
+                                    rgb.ctypes.data_as(u8p), _p(sums) if want_sums else None, C.byref(st))
         return rgb, sums, st.as_dict()
     assert rng_mode == RNG_RAND15 and not early_out and not want_sums
     stats = np.zeros(3, dtype=np.float64)
+    if shading is not None:
+        ref().ref_render_rows_param(_p(centres), _p(radii), len(radii), _p(cam12), W, H, spp, max_depth, seed,
+                                    C.byref(shading), j0, j1, nthreads, rgb.ctypes.data_as(u8p), _p(stats))
+        return rgb, None, {"samples": stats[0], "casts": stats[1], "black": stats[2]}
     ref().ref_render_rows(_p(centres), _p(radii), len(radii), _p(cam12), W, H, spp, max_depth, seed, j0, j1, nthreads,
                           rgb.ctypes.data_as(u8p), _p(stats))
     return rgb, None, {"samples": stats[0], "casts": stats[1], "black": stats[2]}
@@ -148,7 +176,8 @@ def sphere_hit_batch(which, centre, radius, org, dirs, tmin=0.0, tmax=float("inf
     return hit, rec
 
 
-def ray_color_batch(which, centres, radii, org, dirs, seeds, depth, rng_mode=RNG_RAND15, early_out=False):
+def ray_color_batch(which, centres, radii, org, dirs, seeds, depth, rng_mode=RNG_RAND15, early_out=False,
+                    shading: OrcShading | None = None):
     centres, radii = _f64(centres).reshape(-1, 3), _f64(radii)
     org, dirs = _f64(org).reshape(-1, 3), _f64(dirs).reshape(-1, 3)
     seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
@@ -156,10 +185,15 @@ def ray_color_batch(which, centres, radii, org, dirs, seeds, depth, rng_mode=RNG
     rgb = np.empty((n, 3), dtype=np.float64)
     if which == "orc":
         st = OrcStats()
-        oracle().orc_ray_color_batch(_p(centres), _p(radii), len(radii), _p(org), _p(dirs), seeds.ctypes.data_as(u64p),
-                                     rng_mode, int(early_out), n, depth, _p(rgb), C.byref(st))
+        oracle().orc_ray_color_batch_ex(_p(centres), _p(radii), len(radii), _p(org), _p(dirs), seeds.ctypes.data_as(u64p),
+                                        rng_mode, int(early_out), C.byref(shading) if shading is not None else None, n,
+                                        depth, _p(rgb), C.byref(st))
         return rgb, st.as_dict()
     assert rng_mode == RNG_RAND15 and not early_out
+    if shading is not None:
+        ref().ref_ray_color_param_batch(_p(centres), _p(radii), len(radii), _p(org), _p(dirs), seeds.ctypes.data_as(u64p),
+                                        C.byref(shading), n, depth, _p(rgb))
+        return rgb, None
     ref().ref_ray_color_batch(_p(centres), _p(radii), len(radii), _p(org), _p(dirs), seeds.ctypes.data_as(u64p), n, depth,
                               _p(rgb))
     return rgb, None

@@ -24,14 +24,27 @@ def test_library_exports_every_declared_symbol(rt):
     L = rt.lib()
     for name in _header_functions():
         assert hasattr(L, name), name
-    assert L.rt_abi_version() == 2
+    assert L.rt_abi_version() == rt.ABI_VERSION == 3
 
 
 def test_struct_layouts(rt):
     assert C.sizeof(rt.RtCamera) == 96
-    assert C.sizeof(rt.RtParams) == 64
+    assert C.sizeof(rt.RtParams) == 128   # ABI 3: + custom_shading, scatter_mode, albedo, sky_a[3], sky_b[3]
     assert C.sizeof(rt.RtStats) == 88
     assert C.sizeof(rt.RtTileLayout) == 32
+
+
+def test_params_init_fills_the_reference_constants(rt):
+    """rt_params_init: tmin 0 (main.cc:40), hemisphere scatter (:42), albedo 0.5 (:43), sky (:48); custom_shading off."""
+    p = rt.make_params(400, 225, 100, 50)
+    assert (p.width, p.height, p.spp, p.max_depth, p.tmin, p.jitter, p.shard_count) == (400, 225, 100, 50, 0.0, 1, 1)
+    assert p.custom_shading == 0 and p.scatter_mode == rt.SCATTER_HEMISPHERE and p.albedo == 0.5
+    assert list(p.sky_a) == [1.0, 1.0, 1.0] and list(p.sky_b) == [0.5, 0.7, 1.0]
+    q = rt.make_params(400, 225, 100, 50, albedo=0.7, scatter_mode=rt.SCATTER_LAMBERTIAN)
+    assert q.custom_shading == 1 and q.albedo == 0.7 and list(q.sky_b) == [0.5, 0.7, 1.0]
+    for bad in (dict(albedo=1.5), dict(albedo=float("nan")), dict(sky_a=(2.0, 0, 0)), dict(scatter_mode=7)):
+        with pytest.raises(rt.RtError):
+            rt.tile_layout(rt.make_params(64, 64, 1, **bad))
 
 
 def test_tile_layout_host_only(rt):
