@@ -109,6 +109,7 @@ typedef struct {
     uint64_t primary_hits;
     uint64_t overflows;          /* casts that fell back to the full FP64 scan (candidate list full) */
     uint64_t launches;           /* kernels launched by this call */
+    uint64_t self_resolved;      /* BVH mode: casts decided by the start-sphere test + tie grid, without a traversal */
 } rt_stats;
 
 typedef struct {

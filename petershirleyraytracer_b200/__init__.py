@@ -48,7 +48,7 @@ class RtParams(C.Structure):
 class RtStats(C.Structure):
     _fields_ = [("kernel_ms", C.c_double)] + [(n, C.c_uint64) for n in (
         "samples", "casts", "sphere_tests", "node_tests", "exact_tests", "black", "early_outs", "primary_hits",
-        "overflows", "launches")]
+        "overflows", "launches", "self_resolved")]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -176,7 +176,7 @@ class Camera:
 
 def make_params(width: int, height: int, spp: int, max_depth: int = 50, seed: int = 0, tmin: float = 0.0,
                 jitter: bool = True, early_out: bool = True, scan_mode: int = SCAN_AUTO, shard_rank: int = 0,
-                shard_count: int = 1, paths_per_lane: int = 0, chunks: int = 0, cull_smem: bool = False,
+                shard_count: int = 1, paths_per_lane: int = 0, chunks: int = 0, cull_smem: bool = False, variant: int = 0,
                 albedo: float | None = None, sky_a=None, sky_b=None, scatter_mode: int | None = None) -> RtParams:
     """rt_params.  albedo / sky_a / sky_b / scatter_mode (any of them given) switch custom_shading on; left alone, the
     render uses the reference's constants (programs/main.cc:42,43,48)."""
@@ -197,7 +197,9 @@ def make_params(width: int, height: int, spp: int, max_depth: int = 50, seed: in
     p.shard_rank, p.shard_count = shard_rank, shard_count
     p.reserved[0] = paths_per_lane  # tuning knob: paths per lane (0 = default)
     p.reserved[1] = chunks          # tuning knob: sample chunks per tile (0 = auto)
-    p.reserved[2] = 1 if cull_smem else 0  # A/B knob: cull array from TMA-staged shared memory instead of the constant bank
+    # A/B knobs: 1 = cull array from TMA-staged shared memory instead of the constant bank; 2 = BVH mode through the
+    # round-1 one-path-per-lane traversal kernel; 3 = BVH mode without the tie-grid fast path
+    p.reserved[2] = variant if variant else (1 if cull_smem else 0)
     return p
 
 

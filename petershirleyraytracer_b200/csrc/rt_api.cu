@@ -61,6 +61,9 @@ struct rt_scene {
     int32_t* d_bvh_leaf = nullptr;
     int bvh_nodes = 0;
     rt::BvhHost bvh_host;             // topology kept for rt_update_scene's refit
+    rt::TieGridHost tie;              // tie grid of the current sphere positions (rt_bvh.h)
+    float4* d_sph32 = nullptr;        // FP32 {centre, |r|} per sphere (tie grid shell tests)
+    int4* d_tie_cells = nullptr; size_t tie_cells_cap = 0;
     unsigned int* d_tile_counter = nullptr;   // work-queue head of the persistent warps
     unsigned long long* d_stats = nullptr;
     void* d_accum = nullptr; size_t accum_cap = 0;   // fixed-point radiance per tile pixel (+ chunk counters behind it)
@@ -152,6 +155,14 @@ rt::SceneDev scene_dev(const rt_scene* sc, int mode) {
     d.filt = sc->d_filt; d.exact = sc->d_exact; d.inv_r = sc->d_inv_r; d.n = sc->n;
     d.npad = (mode == RT_SCAN_FILTERED) ? sc->npad : 0;  // EXACT / BVH stage nothing
     d.bvh_nodes = sc->d_bvh_nodes; d.bvh_leaf = sc->d_bvh_leaf;
+    const rt::TieGridHost& g = sc->tie;
+    d.sph32 = sc->d_sph32; d.tie_cells = sc->d_tie_cells;
+    d.tie_ok = (g.ok && sc->d_sph32 && sc->d_tie_cells) ? 1 : 0;
+    for (int a = 0; a < 3; ++a) { d.tie_g0[a] = g.g0[a]; d.tie_g1[a] = g.g1[a]; }
+    d.tie_inv_h = g.inv_h; d.tie_rho_max = g.rho_max;
+    d.tie_dimx = g.dim[0]; d.tie_dimy = g.dim[1];
+    d.tie_ngiants = g.n_giants;
+    for (int i = 0; i < 4; ++i) d.tie_giants[i] = g.giants[i];
     return d;
 }
 
@@ -174,6 +185,7 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     rt::RenderArgs a;
     std::memset(&a, 0, sizeof a);
     a.sc = scene_dev(sc, mode);
+    if (p->reserved[2] == 3) a.sc.tie_ok = 0;   // A/B knob: BVH mode without the tie-grid fast path
     for (int c = 0; c < 3; ++c) {
         a.cam_org[c] = cam->origin[c]; a.cam_llc[c] = cam->lower_left_corner[c];
         a.cam_hor[c] = cam->horizontal[c]; a.cam_ver[c] = cam->vertical[c];
@@ -210,9 +222,10 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
         RT_CUDA(cudaMemcpyToSymbolAsync(rt::c_filt, sc->d_filt, (size_t)(sc->npad + rt::kScanPad) * sizeof(float4), 0,
                                         cudaMemcpyDeviceToDevice, stream));
     }
-    const rt::RenderSmem S = rt::render_smem(use_const ? 0 : a.sc.npad, R);
+    rt::RenderSmem S = rt::render_smem(use_const ? 0 : a.sc.npad, R);
     void (*kern)(const rt::RenderArgs) = nullptr;
-    if (mode == RT_SCAN_BVH) kern = rt::render_kernel<1, 2>;
+    if (mode == RT_SCAN_BVH && p->reserved[2] == 2) kern = rt::render_kernel<1, 2>;   // round-1 traversal kernel (A/B evidence only)
+    else if (mode == RT_SCAN_BVH) { kern = rt::render_wave_kernel; S.total = rt::wave_smem().total; }
     else if (use_const) kern = R == 1 ? rt::render_kernel<1, 1> : (R == 2 ? rt::render_kernel<2, 1> : rt::render_kernel<4, 1>);
     else kern = R == 1 ? rt::render_kernel<1, 0> : (R == 2 ? rt::render_kernel<2, 0> : rt::render_kernel<4, 0>);
     RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
@@ -280,6 +293,7 @@ int finish_render(rt_scene* sc, rt_stats* st) {
     st->exact_tests = h[rt::ST_EXACT_TESTS];
     st->black = h[rt::ST_BLACK]; st->early_outs = h[rt::ST_EARLY_OUTS];
     st->primary_hits = h[rt::ST_PRIMARY_HITS]; st->overflows = h[rt::ST_OVERFLOWS];
+    st->self_resolved = h[rt::ST_SELF_RESOLVED];
     st->launches = sc->last_launches;
     return RT_OK;
 }
@@ -326,6 +340,7 @@ int fill_scene(rt_scene* sc, const double* centres_xyz, const double* radii, boo
         cudaFree(sc->d_bvh_nodes); cudaFree(sc->d_bvh_leaf);
         sc->d_bvh_nodes = nullptr; sc->d_bvh_leaf = nullptr; sc->bvh_nodes = 0;
         sc->bvh_host = rt::BvhHost();
+        sc->tie = rt::TieGridHost();
         return RT_OK;
     }
     const bool have_tree = sc->d_bvh_nodes && !sc->bvh_host.nodes.empty();
@@ -346,6 +361,19 @@ int fill_scene(rt_scene* sc, const double* centres_xyz, const double* radii, boo
     if (!bvh.leaf_idx.empty() &&
         cudaMemcpy(sc->d_bvh_leaf, bvh.leaf_idx.data(), bvh.leaf_idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess)
         return RT_ERR_CUDA;
+    // tie grid (start-sphere fast path of the BVH mode), rebuilt for the current positions
+    rt::build_tie_grid(centres_xyz, radii, n, &sc->tie);
+    if (sc->tie.ok) {
+        const size_t cb = sc->tie.cells.size() * sizeof(int32_t);
+        if (cb > sc->tie_cells_cap) {
+            cudaFree(sc->d_tie_cells); sc->d_tie_cells = nullptr; sc->tie_cells_cap = 0;
+            if (cudaMalloc(&sc->d_tie_cells, cb) != cudaSuccess) return RT_ERR_CUDA;
+            sc->tie_cells_cap = cb;
+        }
+        if (cudaMemcpy(sc->d_tie_cells, sc->tie.cells.data(), cb, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(sc->d_sph32, sc->tie.sph.data(), (size_t)(n > 0 ? n : 1) * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess)
+            return RT_ERR_CUDA;
+    }
     return RT_OK;
 }
 
@@ -400,6 +428,7 @@ int rt_upload_scene(const double* centres_xyz, const double* radii, int32_t n, i
         if (cudaMalloc(&sc->d_filt, nf * sizeof(float4)) != cudaSuccess ||
             cudaMalloc(&sc->d_exact, ne * sizeof(double4)) != cudaSuccess ||
             cudaMalloc(&sc->d_inv_r, ne * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&sc->d_sph32, ne * sizeof(float4)) != cudaSuccess ||
             cudaMalloc(&sc->d_tile_counter, sizeof(unsigned int)) != cudaSuccess ||
             cudaMalloc(&sc->d_stats, rt::kNumStats * sizeof(unsigned long long)) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
         if (cudaEventCreate(&sc->ev0) != cudaSuccess || cudaEventCreate(&sc->ev1) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
@@ -435,7 +464,7 @@ void rt_free_scene(rt_scene* sc) {
     DeviceGuard guard(sc->device);
     if (sc->pending) cudaEventSynchronize(sc->ev1);
     cudaFree(sc->d_filt); cudaFree(sc->d_exact); cudaFree(sc->d_inv_r); cudaFree(sc->d_tile_counter); cudaFree(sc->d_stats);
-    cudaFree(sc->d_bvh_nodes); cudaFree(sc->d_bvh_leaf);
+    cudaFree(sc->d_bvh_nodes); cudaFree(sc->d_bvh_leaf); cudaFree(sc->d_sph32); cudaFree(sc->d_tie_cells);
     cudaFree(sc->d_frame); cudaFree(sc->d_sum); cudaFree(sc->d_accum);
     if (sc->ev0) cudaEventDestroy(sc->ev0);
     if (sc->ev1) cudaEventDestroy(sc->ev1);
@@ -657,7 +686,7 @@ static int ray_color_impl(const rt_scene* scene, const double* org, const double
         st->samples = h[rt::ST_SAMPLES]; st->casts = h[rt::ST_CASTS]; st->exact_tests = h[rt::ST_EXACT_TESTS];
         st->sphere_tests = mode == RT_SCAN_FILTERED ? h[rt::ST_CASTS] * (uint64_t)sc->n : 0;
         st->black = h[rt::ST_BLACK]; st->early_outs = h[rt::ST_EARLY_OUTS]; st->primary_hits = h[rt::ST_PRIMARY_HITS];
-        st->overflows = h[rt::ST_OVERFLOWS]; st->launches = 1;
+        st->overflows = h[rt::ST_OVERFLOWS]; st->self_resolved = h[rt::ST_SELF_RESOLVED]; st->launches = 1;
     }
     return RT_OK;
 }

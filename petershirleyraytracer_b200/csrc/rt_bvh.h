@@ -338,4 +338,143 @@ inline void build_bvh(const double* centres, const double* radii, int n, BvhHost
     collapse_bvh4(out);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Tie grid: "which spheres' surfaces pass (numerically) through this point?"  answered in O(1).
+//
+// With the reference's tmin = 0 (programs/main.cc:40) 86 % of all ray casts of the book scene start ON the sphere
+// the path just hit and hit that sphere again at t == 0 exactly (the self-hit artefact).  For such a
+// cast hittable_list::hit (programs/hittable_list.cc:3-20) can only return another sphere j if j ALSO yields an
+// accepted root <= that t (ties go to the later index), which requires the ray origin o to lie on j's surface up to
+// rounding: sphere::hit's root (programs/sphere.cc:24,29) is <= t only if dist(o, surface_j) <= t * |dir|, and a
+// root of exactly 0 only if |C_j| = ||o - c_j|^2 - r_j^2| is below ~2^-49 (|o| + |c_j|)^2.  The device therefore
+// runs the FP64 test of the start sphere first and, when it returns t ~ 0, decides the whole cast with a conservative
+// FP32 shell test  | |o - c_j|^2 - r_j^2 | <= tol_j(o) + reach  on the few spheres whose surface can come near o
+// (FP64 sphere::hit on those that pass) -- no traversal.  Candidates: up to kTieGiants "giant" spheres (tested for
+// every such cast) plus the <= 4 spheres listed in the uniform-grid cell that contains o.  A sphere is listed in every
+// cell its padded bounding box overlaps; the padding covers the shell tolerance at the grid's largest |o|, the largest
+// reach the device accepts (rho_max), the FP32 rounding of o and of the cell arithmetic.  Cells that would need
+// more than four entries carry kTieOverfull and send the cast to the BVH traversal instead (always correct).
+constexpr int kTieGiants = 4;
+constexpr int32_t kTieOverfull = -2;
+constexpr double kTieShell = 1.9073486328125e-06;   // 2^-19 = 32 * 2^-24: FP32 error of the shell quantity is <= 2^-24 (14 (o^2 + c^2) + 4 r^2)
+
+struct TieGridHost {
+    bool ok = false;             // false: no fast path for this scene (every cast takes the traversal)
+    float g0[3] = {0, 0, 0}, g1[3] = {0, 0, 0};   // grid bounds (outside: no non-giant sphere can be a candidate)
+    float inv_h = 0.f, rho_max = 0.f;
+    int dim[3] = {0, 0, 0};
+    int n_giants = 0;
+    int32_t giants[kTieGiants] = {-1, -1, -1, -1};
+    std::vector<int32_t> cells;  // 4 per cell: sphere indices, -1 = unused; cells[4 i] == kTieOverfull: undecidable here
+    std::vector<float> sph;      // 4 per sphere: cx, cy, cz, |r| rounded to nearest
+};
+
+inline void build_tie_grid(const double* c, const double* r, int n, TieGridHost* out) {
+    *out = TieGridHost();
+    out->sph.resize((size_t)4 * (n > 0 ? n : 1));
+    if (n <= 0) return;
+    std::vector<double> rad((size_t)n);
+    double cmax = 0.0;
+    for (int k = 0; k < n; ++k) {
+        rad[(size_t)k] = std::fabs(r[k]);
+        for (int a = 0; a < 3; ++a) { out->sph[4 * (size_t)k + a] = (float)c[3 * k + a]; cmax = std::max(cmax, std::fabs(c[3 * k + a])); }
+        out->sph[4 * (size_t)k + 3] = (float)rad[(size_t)k];
+        if (!std::isfinite(c[3 * k]) || !std::isfinite(c[3 * k + 1]) || !std::isfinite(c[3 * k + 2]) || !std::isfinite(r[k])) return;
+    }
+    std::vector<double> sorted(rad);
+    std::nth_element(sorted.begin(), sorted.begin() + n / 2, sorted.end());
+    const double r_med = sorted[(size_t)n / 2];
+    if (!(r_med >= 1e-12) || !(cmax <= 1e12)) return;   // FP32 shell arithmetic needs moderate magnitudes
+
+    double h = 2.0 * r_med;
+    for (int attempt = 0; attempt < 24; ++attempt, h *= 2.0) {
+        const double rho_max = h / 64.0;
+        // pass 1: giants (by the number of cells their box would cover) and the bounds of everything else
+        std::vector<char> giant((size_t)n, 0);
+        int ng = 0;
+        double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int k = 0; k < n; ++k) {
+            const double cells_axis = 2.0 * rad[(size_t)k] / h + 2.0;
+            if (cells_axis * cells_axis * cells_axis > 1000.0) { giant[(size_t)k] = 1; ++ng; continue; }   // > 8 cells across
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = std::min(lo[a], c[3 * k + a] - rad[(size_t)k]);
+                hi[a] = std::max(hi[a], c[3 * k + a] + rad[(size_t)k]);
+            }
+        }
+        if (ng > kTieGiants) continue;
+        TieGridHost g;
+        g.sph = out->sph;
+        g.n_giants = ng;
+        for (int k = 0, i = 0; k < n; ++k) if (giant[(size_t)k]) g.giants[i++] = k;
+        g.rho_max = bvh_detail::down(rho_max);
+        if (ng == n) {   // nothing but giants: an empty grid (every o is "outside")
+            g.dim[0] = g.dim[1] = g.dim[2] = 0; g.inv_h = 0.f;
+            g.g0[0] = g.g0[1] = g.g0[2] = INFINITY; g.g1[0] = g.g1[1] = g.g1[2] = -INFINITY;
+            g.cells.assign(4, -1);
+            g.ok = true;
+            *out = g;
+            return;
+        }
+        // largest |o| inside the (generously padded) grid, for the shell tolerance the padding must cover
+        double omax2 = 0.0;
+        for (int a = 0; a < 3; ++a) { const double m = std::max(std::fabs(lo[a]), std::fabs(hi[a])) + 2.0 * h; omax2 += m * m; }
+        const double omax = std::sqrt(omax2);
+        const double delta = 0.02 * h + 4.76837158203125e-07 * (omax + h);   // FP32 rounding of o and of the cell arithmetic (2^-21 |o|)
+        std::vector<double> pad((size_t)n, 0.0);
+        double pad_max = 0.0;
+        for (int k = 0; k < n; ++k) {
+            if (giant[(size_t)k]) continue;
+            const double c2 = c[3 * k] * c[3 * k] + c[3 * k + 1] * c[3 * k + 1] + c[3 * k + 2] * c[3 * k + 2], r2 = rad[(size_t)k] * rad[(size_t)k];
+            const double T = 2.0 * kTieShell * (1.01 * omax2 + c2 + r2);                 // >= tol_j(o) for every o in the grid
+            const double reach = rho_max * (2.0 * rad[(size_t)k] + rho_max) * 1.01;      // the reach term of the device test
+            pad[(size_t)k] = std::sqrt(r2 + T + reach) - rad[(size_t)k] + rho_max + delta;
+            pad_max = std::max(pad_max, pad[(size_t)k]);
+        }
+        double ext[3];
+        long long total = 1;
+        bool fits = true;
+        for (int a = 0; a < 3; ++a) {
+            lo[a] -= pad_max + 0.5 * h; hi[a] += pad_max + 0.5 * h;
+            g.g0[a] = bvh_detail::down(lo[a]);
+            ext[a] = hi[a] - (double)g.g0[a];
+            const double cells_d = std::ceil(ext[a] / h) + 1.0;
+            if (!(cells_d < 1e6)) { fits = false; break; }
+            g.dim[a] = (int)cells_d;
+            total *= g.dim[a];
+            if (total > (1ll << 21)) { fits = false; break; }
+        }
+        if (!fits) continue;
+        g.inv_h = (float)(1.0 / h);
+        const double hf = 1.0 / (double)g.inv_h;   // the cell size the device effectively uses
+        for (int a = 0; a < 3; ++a) g.g1[a] = bvh_detail::down((double)g.g0[a] + (g.dim[a] - 0.5) * hf);   // strictly inside the last cell
+        g.cells.assign((size_t)total * 4, -1);
+        size_t overfull = 0;
+        for (int k = 0; k < n; ++k) {
+            if (giant[(size_t)k]) continue;
+            int i0[3], i1[3];
+            for (int a = 0; a < 3; ++a) {
+                const double x0 = (c[3 * k + a] - rad[(size_t)k] - pad[(size_t)k] - (double)g.g0[a]) / hf;
+                const double x1 = (c[3 * k + a] + rad[(size_t)k] + pad[(size_t)k] - (double)g.g0[a]) / hf;
+                i0[a] = std::max(0, (int)std::floor(x0)); i1[a] = std::min(g.dim[a] - 1, (int)std::floor(x1));
+            }
+            for (int z = i0[2]; z <= i1[2]; ++z)
+                for (int y = i0[1]; y <= i1[1]; ++y)
+                    for (int x = i0[0]; x <= i1[0]; ++x) {
+                        int32_t* cell = &g.cells[4 * (((size_t)z * g.dim[1] + y) * g.dim[0] + x)];
+                        if (cell[0] == kTieOverfull) continue;
+                        int e = 0;
+                        while (e < 4 && cell[e] >= 0) ++e;
+                        if (e < 4) cell[e] = k;
+                        else { cell[0] = kTieOverfull; ++overfull; }
+                    }
+        }
+        // a grid where a large part of the occupied cells is overfull decides little: coarser cells do not help
+        // (lists only grow), so accept it as it is -- overfull cells fall back to the traversal
+        (void)overfull;
+        g.ok = true;
+        *out = g;
+        return;
+    }
+}
+
 }  // namespace rt

@@ -26,7 +26,7 @@ constexpr int kFixShift = 44;       // radiance accumulates as 20.44 fixed point
 constexpr int kNumStats = 10;
 
 enum StatSlot { ST_SAMPLES = 0, ST_CASTS, ST_SPHERE_TESTS, ST_NODE_TESTS, ST_EXACT_TESTS, ST_BLACK, ST_EARLY_OUTS,
-                ST_PRIMARY_HITS, ST_OVERFLOWS, ST_UNUSED };
+                ST_PRIMARY_HITS, ST_OVERFLOWS, ST_SELF_RESOLVED };
 
 // error-bound constants of the FP32 cull (see DESIGN.md "cull error bound"): with S = |c| + |o| and u = 2^-24,
 // |D_fp32 - D| <= u * (19 S^2 + 4 r^2) <= u * (38 |c|^2 + 38 |o|^2 + 4 r^2)  [b: 5uS -> b^2: 10uS^2; inputs of
@@ -109,6 +109,13 @@ struct SceneDev {
     int n, npad;
     const float4* bvh_nodes;   // 2 float4 per child, kBvhW children per node (rt_bvh.h: Bvh4Node), root = node 0; NULL if not built
     const int32_t* bvh_leaf;   // sphere list indices, leaf by leaf
+    // tie grid (rt_bvh.h: TieGridHost): O(1) answer to "which spheres' surfaces pass through this point"
+    const float4* sph32;       // n entries {cx, cy, cz, |r|} in FP32
+    const int4* tie_cells;     // 4 sphere indices per cell (-1 unused; .x == -2: overfull, undecidable)
+    float tie_g0[3], tie_g1[3], tie_inv_h, tie_rho_max;
+    int tie_dimx, tie_dimy;
+    int tie_ok, tie_ngiants;
+    int tie_giants[4];
 };
 
 // The constants programs/main.cc hard-codes in ray_color, as launch arguments (rt_params).
@@ -403,11 +410,11 @@ __device__ __forceinline__ bool exact_test_unordered(const double4* __restrict__
 #endif
 constexpr int kBvhW = RT_BVH_WIDTH;  // children per device BVH node (== rt_bvh.h: kBvhWidth)
 constexpr int kBvhStack = 48;
-__device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double oy, double oz, double dx, double dy,
-                                         double dz, double A, double tmin, double tmax, uint32_t& n_exact,
-                                         uint32_t& n_nodes, bool& overflow) {
-    Best best;
-    best.t = tmax; best.C = 1.0; best.k = -1;
+// `best` is in/out: a hit already known (the start sphere's, see tie_resolve) bounds the traversal from the first
+// node on; `skip` names a sphere that needs no further test (that start sphere; -1: none).
+__device__ __forceinline__ void bvh_cast(const SceneDev& sc, double ox, double oy, double oz, double dx, double dy,
+                                         double dz, double A, double tmin, double tmax, Best& best, int skip,
+                                         uint32_t& n_exact, uint32_t& n_nodes, bool& overflow) {
     const RcpA dA = make_rcp(A);
     // (An FP32 line test per leaf sphere before the FP64 test was measured: exact tests/cast 4.96 -> 1.21,
     //  but 6 % slower overall -- the per-cast cull constants cost more than the FP64 tests they save.)
@@ -432,7 +439,7 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
         if ((!zx && fabsf((float)dx) < kMinNormal) || (!zy && fabsf((float)dy) < kMinNormal) ||
             (!zz && fabsf((float)dz) < kMinNormal)) {
             overflow = true;
-            return best;
+            return;
         }
     }
     const float ivx = zx ? 0.f : __frcp_rn((float)dx), ivy = zy ? 0.f : __frcp_rn((float)dy),
@@ -453,7 +460,7 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
     // the pruning bound: entry distance tn may matter iff tn * (1 - 2^-19) <= RU(best t); kept pre-divided (rounded
     // up, so the test only gets looser) so that a box costs one compare against it
     const float kInvDn = 1.0f + 3.814697265625e-06f;  // > 1 / (1 - 2^-19)
-    float bu = __fmul_ru(__double2float_ru(tmax), kInvDn);
+    float bu = __fmul_ru(__double2float_ru(best.k >= 0 ? best.t : tmax), kInvDn);
     int stack_n[kBvhStack];
     float stack_t[kBvhStack];
     int sp = 0, node = 0;
@@ -506,13 +513,16 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
                 {   // single-sphere leaves: no loop over the leaf (its branch overhead was ~4 % of the traversal)
                     (void)count;
                     const int k = first;   // (single-sphere leaves carry the sphere index itself, rt_bvh.h)
-                    ++n_exact;
-                    if (exact_test_unordered(sc.exact, k, ox, oy, oz, dx, dy, dz, dA, tmin, tmax, best))
-                        bu = __fmul_ru(__double2float_ru(best.t), kInvDn);
+                    if (k != skip) {
+                        ++n_exact;
+                        if (exact_test_unordered(sc.exact, k, ox, oy, oz, dx, dy, dz, dA, tmin, tmax, best))
+                            bu = __fmul_ru(__double2float_ru(best.t), kInvDn);
+                    }
                 }
 #else
                 for (int j = 0; j < count; ++j) {
                     const int k = __ldg(sc.bvh_leaf + first + j);
+                    if (k == skip) continue;
                     ++n_exact;
                     if (exact_test_unordered(sc.exact, k, ox, oy, oz, dx, dy, dz, dA, tmin, tmax, best))
                         bu = __fmul_ru(__double2float_ru(best.t), kInvDn);
@@ -534,7 +544,7 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
                     pn = on; pt = ot;
                 }
                 if (pn >= 0) {
-                    if (sp >= kBvhStack) { overflow = true; return best; }
+                    if (sp >= kBvhStack) { overflow = true; return; }
                     stack_n[sp] = pn; stack_t[sp] = pt; ++sp;
                 }
             }
@@ -550,7 +560,76 @@ __device__ __forceinline__ Best bvh_cast(const SceneDev& sc, double ox, double o
             if (!found) break;
         }
     }
-    return best;
+}
+
+// ---------------------------------------------------------------- start-sphere test + tie grid (rt_bvh.h: TieGridHost)
+// A cast that starts on the sphere the path just hit (`self`) and hits it again at t ~ 0 -- 86 % of the reference's
+// casts on the book scene, the tmin = 0 artefact of programs/main.cc:40 -- is decided here without a traversal:
+// another sphere j can only replace that hit if it yields an accepted root <= t (programs/hittable_list.cc:11-15),
+// which needs its surface within reach = t * |dir| of the origin.  Conservative FP32 shell test
+//     | |o - c_j|^2 - r_j^2 |  <=  2^-19 (|o|^2 + |c_j|^2 + r_j^2)  +  reach (2 r_j + reach)
+// (the first term covers the FP32 evaluation error 2^-24 (14 (o^2 + c^2) + 4 r^2) with a factor 2 to spare and,
+// by 30 binary orders, the band in which sphere::hit can round a root to 0) on the giants and on the <= 4 spheres
+// listed in the grid cell of o; those that pass run the FP64 sphere::hit and are merged with the reference's tie rule.
+// Returns false if the cast cannot be decided here (reach too long, overfull cell): the caller traverses with
+// `best` as the initial bound.
+__device__ __forceinline__ bool tie_candidate(const float4 s, float fx, float fy, float fz, float o2, float rho) {
+    const float ex = fx - s.x, ey = fy - s.y, ez = fz - s.z;
+    const float q = fmaf(-s.w, s.w, fmaf(ex, ex, fmaf(ey, ey, ez * ez)));
+    const float w = fmaf(s.x, s.x, fmaf(s.y, s.y, fmaf(s.z, s.z, s.w * s.w)));
+    const float tol = fmaf(1.9073486328125e-06f, o2 + w, rho * fmaf(2.0002f, s.w, rho));
+    return !(fabsf(q) > tol);   // (NaN counts as a candidate)
+}
+
+__device__ __forceinline__ bool tie_resolve(const SceneDev& sc, int self, double ox, double oy, double oz, double dx,
+                                            double dy, double dz, const RcpA& dA, double tmin, Best& best,
+                                            uint32_t& n_exact) {
+    const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+    float rho = 0.f;
+    if (best.t != 0.0) {   // reach = t * |dir|, rounded up
+        rho = __fmul_ru(__fmul_ru(__double2float_ru(best.t), __fsqrt_ru(__double2float_ru(dA.A))), 1.0000019f);
+        if (!(rho <= sc.tie_rho_max)) return false;   // (also NaN / negative t)
+    }
+    const float fx = (float)ox, fy = (float)oy, fz = (float)oz;
+    const float o2 = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
+#pragma unroll 1
+    for (int g = 0; g < sc.tie_ngiants; ++g) {
+        const int j = sc.tie_giants[g];
+        if (j != self && tie_candidate(__ldg(sc.sph32 + j), fx, fy, fz, o2, rho)) {
+            ++n_exact;
+            exact_test_unordered(sc.exact, j, ox, oy, oz, dx, dy, dz, dA, tmin, kInf, best);
+        }
+    }
+    const bool inside = fx >= sc.tie_g0[0] && fx <= sc.tie_g1[0] && fy >= sc.tie_g0[1] && fy <= sc.tie_g1[1] &&
+                        fz >= sc.tie_g0[2] && fz <= sc.tie_g1[2];
+    if (inside) {   // outside the grid no listed sphere has its (padded) box around o
+        const int ix = (int)((fx - sc.tie_g0[0]) * sc.tie_inv_h), iy = (int)((fy - sc.tie_g0[1]) * sc.tie_inv_h),
+                  iz = (int)((fz - sc.tie_g0[2]) * sc.tie_inv_h);
+        const int4 cell = __ldg(sc.tie_cells + ((size_t)iz * sc.tie_dimy + iy) * sc.tie_dimx + ix);
+        if (cell.x == -2) return false;
+        const int js[4] = {cell.x, cell.y, cell.z, cell.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = js[e];
+            if (j >= 0 && j != self && tie_candidate(__ldg(sc.sph32 + j), fx, fy, fz, o2, rho)) {
+                ++n_exact;
+                exact_test_unordered(sc.exact, j, ox, oy, oz, dx, dy, dz, dA, tmin, kInf, best);
+            }
+        }
+    }
+    return true;
+}
+
+// The part of a BVH-mode cast that needs no traversal: FP64 sphere::hit of the start sphere, then the tie grid.
+// Returns true if `best` is the cast's final answer.
+__device__ __forceinline__ bool self_cast(const SceneDev& sc, int self, double ox, double oy, double oz, double dx,
+                                          double dy, double dz, double A, double tmin, Best& best, uint32_t& n_exact) {
+    if (self < 0) return false;
+    const RcpA dA = make_rcp(A);
+    ++n_exact;
+    exact_test_unordered(sc.exact, self, ox, oy, oz, dx, dy, dz, dA, tmin, __longlong_as_double(0x7ff0000000000000ll), best);
+    if (!(sc.tie_ok && best.k == self && dA.fast)) return false;
+    return tie_resolve(sc, self, ox, oy, oz, dx, dy, dz, dA, tmin, best, n_exact);
 }
 
 // hittable_list::hit for one ray given its survivors (or the full list when ovf): list order, shrinking tmax.

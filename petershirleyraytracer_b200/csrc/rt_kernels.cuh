@@ -344,7 +344,8 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R>::kMinBlocks) render_
                 ovf[r] = live && !(sane && a.tmin >= 0.0);  // such rays take the sequential FP64 scan
                 if (live && !ovf[r]) {
                     bool deep = false;
-                    pending[r] = bvh_cast(a.sc, ox, oy, oz, dx, dy, dz, A, a.tmin, kInf, n_exact, n_nodes, deep);
+                    pending[r].t = kInf; pending[r].C = 1.0; pending[r].k = -1;
+                    bvh_cast(a.sc, ox, oy, oz, dx, dy, dz, A, a.tmin, kInf, pending[r], -1, n_exact, n_nodes, deep);
                     ovf[r] = deep;  // traversal stack exhausted (degenerate tree): sequential scan instead
                 }
             } else {
@@ -363,6 +364,261 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R>::kMinBlocks) render_
     const int slots[8] = {ST_SAMPLES, ST_CASTS, ST_EXACT_TESTS, ST_BLACK, ST_EARLY_OUTS, ST_PRIMARY_HITS, ST_OVERFLOWS, ST_NODE_TESTS};
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
+        unsigned long long v = vals[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&a.stats[slots[c]], v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// render_wave_kernel: the BVH mode (RT_SCAN_BVH, the RT_SCAN_AUTO default from 16 spheres up).
+//
+// The linear-scan kernel above keeps one path per (lane, slot) and runs every lane through the same steps; with a
+// tree that costs SIMT efficiency twice over: lanes leave the traversal loop after different numbers of node visits
+// (14.5 of 32 threads active per instruction in round 1, profiles/r1p_bvh_kernel_summary.txt), and 86 % of the
+// reference's casts do not need a traversal at all (self_cast above).  Here every WARP owns a pool of kPool path
+// records in shared memory and three index queues; each round it runs ONE phase on up to 32 records of one queue:
+//   S  consume the record's cast result -- sky + accumulate (programs/main.cc:46-48), early-out, or hit_record +
+//      scatter (sphere.cc:34-36, main.cc:42-43) -- then start the next cast: FP64 sphere::hit of the sphere the new
+//      ray starts on and the tie grid.  Decided casts (86-91 % on the book scene) stay in S, the rest go to T.
+//   T  4-wide BVH traversal bounded by the start sphere's hit, then back to S.
+//   regeneration: freed records take the warp's next (pixel, sample) ids and enter T as primary rays.
+// The queues compact: each phase runs with (nearly) all 32 lanes whatever mix of trapped, escaping and new paths
+// the pool holds.  Radiance sums, units, chunk bookkeeping and write_color are the linear-scan kernel's.
+constexpr int kPool = 64;   // path records per warp
+
+struct WaveSmem { uint32_t acc_off, state_off, meta_off, bt_off, bk_off, self_off, q_off, total; };
+__host__ __device__ inline WaveSmem wave_smem() {
+    WaveSmem L;
+    L.acc_off = 0;
+    L.state_off = L.acc_off + kWarps * 2 * kTilePix * 3 * 8;
+    L.meta_off = L.state_off + kWarps * 6 * kPool * 8;
+    L.bt_off = L.meta_off + kWarps * kPool * 16;
+    L.bk_off = L.bt_off + kWarps * kPool * 8;
+    L.self_off = L.bk_off + kWarps * kPool * 4;
+    L.q_off = L.self_off + kWarps * kPool * 4;
+    L.total = L.q_off + kWarps * 3 * kPool;
+    return L;
+}
+
+#ifndef RT_WAVE_MINB
+#define RT_WAVE_MINB 5
+#endif
+__global__ void __launch_bounds__(kThreads, RT_WAVE_MINB) render_wave_kernel(const __grid_constant__ RenderArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const WaveSmem L = wave_smem();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(smem + L.acc_off) + warp * (2 * kTilePix * 3);
+    double* st = reinterpret_cast<double*>(smem + L.state_off) + warp * (6 * kPool);   // component c of record i: st[c*kPool + i]
+    uint4* meta = reinterpret_cast<uint4*>(smem + L.meta_off) + warp * kPool;          // pixel id, sample, next Philox block, depth | (pixel-in-tile | buffer << 6) << 16
+    double* bt = reinterpret_cast<double*>(smem + L.bt_off) + warp * kPool;             // pending cast result: t ...
+    int32_t* bk = reinterpret_cast<int32_t*>(smem + L.bk_off) + warp * kPool;           // ... sphere index | (C == 0) << 30, or -1 = miss
+    int32_t* selfk = reinterpret_cast<int32_t*>(smem + L.self_off) + warp * kPool;      // sphere the record's ray starts on (-1: camera ray)
+    uint8_t* qS = smem + L.q_off + warp * (3 * kPool);
+    uint8_t* qT = qS + kPool;
+    uint8_t* qF = qT + kPool;
+
+#pragma unroll
+    for (int j = 0; j < 2 * kTilePix * 3 / 32; ++j) acc[j * 32 + lane] = 0ull;
+    for (int i = lane; i < kPool; i += 32) qF[i] = (uint8_t)i;
+    int nS = 0, nT = 0, nF = kPool;   // queue lengths (warp-uniform)
+    int infl0 = 0, infl1 = 0;         // records in flight per unit buffer (warp-uniform)
+
+    const double wm1 = (double)(a.W - 1), hm1 = (double)(a.H - 1);
+    const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+    uint32_t n_samples = 0, n_casts = 0, n_exact = 0, n_black = 0, n_early = 0, n_primary = 0, n_ovf = 0, n_nodes = 0, n_self = 0;
+
+    Unit u0, u1;
+    u0.valid = u1.valid = 0; u0.total = u0.next = u1.total = u1.next = 0; u0.tile_l = u1.tile_l = u0.chunk = u1.chunk = 0;
+    int cur = 0;
+    bool no_more = false;
+
+    for (;;) {
+        __syncwarp();   // queue / record writes of the last phase are visible to every lane
+        // ---------------- retire units whose samples are all traced
+        if (u0.valid && u0.next >= u0.total && infl0 == 0) { flush_unit(a, u0, acc, lane); u0.valid = 0; }
+        if (u1.valid && u1.next >= u1.total && infl1 == 0) { flush_unit(a, u1, acc + kTilePix * 3, lane); u1.valid = 0; }
+
+        // ---------------- regeneration: free records take the next (pixel, sample) ids
+        while (nF > 0) {
+            Unit c = cur ? u1 : u0;
+            if (!c.valid || c.next >= c.total) {
+                const int np = c.valid ? (cur ^ 1) : cur;
+                const Unit o = np ? u1 : u0;
+                if (o.valid || no_more) break;   // other buffer draining, or frame exhausted
+                unsigned int id = 0;
+                if (lane == 0) id = atomicAdd(a.unit_counter, 1u);
+                id = __shfl_sync(0xffffffffu, id, 0);
+                if (id >= (unsigned)a.units_local) { no_more = true; break; }
+                c.valid = 1;
+                c.tile_l = (int)(id / (unsigned)a.chunks);
+                c.chunk = (int)(id - (unsigned)c.tile_l * (unsigned)a.chunks);
+                const TileGeom g = tile_geom(a, c.tile_l);
+                c.total = (uint32_t)(g.tw * g.th) * (uint32_t)unit_spp(a, c.chunk);
+                c.next = 0;
+                cur = np;
+            }
+            const uint32_t avail = c.total - c.next;
+            const int m = (int)min((uint32_t)min(nF, 32), avail);
+            if (lane < m) {
+                const TileGeom g = tile_geom(a, c.tile_l);
+                const uint32_t id = c.next + (uint32_t)lane;
+                const uint32_t ns = (uint32_t)unit_spp(a, c.chunk);
+                const uint32_t p = id / ns;
+                const uint32_t s = (uint32_t)(a.sample_base + c.chunk * a.chunk_spp) + (id - p * ns);
+                const int ly = (int)p / g.tw, lx = (int)p - ly * g.tw;
+                const int i = g.x0 + lx, j = a.H - 1 - (g.y0 + ly);  // j from the bottom (programs/main.cc:72)
+                const uint32_t pixid = (uint32_t)(j * a.W + i);
+                double xu = 0.5, xv = 0.5;
+                if (a.jitter) {
+                    const uint4 w = philox4x32_10(pixid, s, 0u, 0u, a.key0, a.key1);
+                    xu = u32_unit(w.x); xv = u32_unit(w.y);
+                }
+                const double u = ddiv(dadd((double)i, xu), wm1);  // programs/main.cc:80
+                const double v = ddiv(dadd((double)j, xv), hm1);  // programs/main.cc:81
+                double dx, dy, dz;
+                camera_ray(a.cam_org, a.cam_llc, a.cam_hor, a.cam_ver, u, v, dx, dy, dz);
+                ++n_samples;
+                if (a.max_depth >= 0) {
+                    const int rec = qF[nF - m + lane];
+                    st[0 * kPool + rec] = a.cam_org[0]; st[1 * kPool + rec] = a.cam_org[1]; st[2 * kPool + rec] = a.cam_org[2];
+                    st[3 * kPool + rec] = dx; st[4 * kPool + rec] = dy; st[5 * kPool + rec] = dz;
+                    meta[rec] = make_uint4(pixid, s, 1u, (uint32_t)a.max_depth | ((uint32_t)((ly * kTileW + lx) | (cur << 6)) << 16));
+                    bt[rec] = kInf; bk[rec] = -1; selfk[rec] = -1;
+                    qT[nT + lane] = (uint8_t)rec;
+                } else {
+                    ++n_black;  // ray_color(r, world, depth < 0) is black without a cast (main.cc:36)
+                }
+            }
+            c.next += (uint32_t)m;
+            if (cur) u1 = c; else u0 = c;
+            if (a.max_depth >= 0) {
+                nF -= m; nT += m;
+                if (cur) infl1 += m; else infl0 += m;
+            }
+        }
+        if (nS == 0 && nT == 0) {
+            if (no_more && !u0.valid && !u1.valid) break;
+            continue;   // units fully claimed and nothing in flight: they retire at the top of the loop
+        }
+        __syncwarp();
+
+        if (nS >= nT) {
+            // ================= S: consume a cast result, shade, start the next cast (start sphere + tie grid)
+            const int m = min(nS, 32);
+            const bool active = lane < m;
+            const int rec = active ? (int)qS[nS - m + lane] : 0;
+            nS -= m;
+            int dest = 0;        // 1: S again (next cast decided here), 2: T, 3: record is free
+            int buf = 0;
+            if (active) {
+                const double ox = st[0 * kPool + rec], oy = st[1 * kPool + rec], oz = st[2 * kPool + rec];
+                const double dx = st[3 * kPool + rec], dy = st[4 * kPool + rec], dz = st[5 * kPool + rec];
+                uint4 mt = meta[rec];
+                const int depth = (int)(mt.w & 0xffffu), lp = (int)(mt.w >> 16);  // lp: bits 0-5 pixel in tile, bit 6 buffer
+                buf = lp >> 6;
+                const int bounces = a.max_depth - depth;
+                const double A = ddot(dx, dy, dz, dx, dy, dz);  // programs/sphere.cc:9
+                const int kk = bk[rec];
+                ++n_casts;
+                if (kk < 0) {
+                    // miss: sky (programs/main.cc:46-48) * attenuation -> fixed-point accumulate
+                    double cr, cg, cb;
+                    sky_color(a.sh, dy, A, bounces, cr, cg, cb);
+                    const double fs = (double)(1ull << kFixShift);
+                    unsigned long long* ap = acc + (buf * kTilePix + (lp & 63)) * 3;
+                    atomicAdd(ap + 0, __double2ull_rz(cr * fs));
+                    atomicAdd(ap + 1, __double2ull_rz(cg * fs));
+                    atomicAdd(ap + 2, __double2ull_rz(cb * fs));
+                    dest = 3;
+                } else {
+                    Best hitb;
+                    hitb.t = bt[rec]; hitb.k = kk & 0x3fffffff; hitb.C = (kk >> 30) & 1 ? 0.0 : 1.0;
+                    if (bounces == 0) ++n_primary;
+                    if (a.early_out && hitb.t == 0.0 && hitb.C == 0.0) {
+                        // origin stays on this sphere with C == 0: every later cast hits at t == 0 -> black
+                        ++n_early; ++n_black;
+                        dest = 3;
+                    } else {
+                        const Record rc = make_record(a.sc, hitb, ox, oy, oz, dx, dy, dz);
+                        double rx, ry, rz;
+                        random_scatter(mt.x, mt.y, mt.z, a.key0, a.key1, rc.nx, rc.ny, rc.nz, a.sh.lambertian, rx, ry, rz);
+                        // programs/main.cc:42-43: target = (p + normal) + rv; next ray = (p, target - p)
+                        const double ndx = dsub(dadd(dadd(rc.px, rc.nx), rx), rc.px);
+                        const double ndy = dsub(dadd(dadd(rc.py, rc.ny), ry), rc.py);
+                        const double ndz = dsub(dadd(dadd(rc.pz, rc.nz), rz), rc.pz);
+                        if (depth == 0) {  // programs/main.cc:36-37: the next ray_color call has depth < 0
+                            ++n_black;
+                            dest = 3;
+                        } else {
+                            st[0 * kPool + rec] = rc.px; st[1 * kPool + rec] = rc.py; st[2 * kPool + rec] = rc.pz;
+                            st[3 * kPool + rec] = ndx; st[4 * kPool + rec] = ndy; st[5 * kPool + rec] = ndz;
+                            mt.w = (uint32_t)(depth - 1) | ((uint32_t)lp << 16);
+                            meta[rec] = mt;
+                            // ---- the next cast: start sphere first (programs/sphere.cc:3-32), then the tie grid
+                            const double A2 = ddot(ndx, ndy, ndz, ndx, ndy, ndz);
+                            const bool sane = A2 > 0.0 && A2 < kInf && (rc.px * rc.px + rc.py * rc.py + rc.pz * rc.pz) < kCullMaxMag2;
+                            Best nb;
+                            nb.t = kInf; nb.C = 1.0; nb.k = -1;
+                            bool decided = false;
+                            if (sane && a.tmin >= 0.0)   // (other rays: the T phase runs the sequential FP64 scan)
+                                decided = self_cast(a.sc, hitb.k, rc.px, rc.py, rc.pz, ndx, ndy, ndz, A2, a.tmin, nb, n_exact);
+                            bt[rec] = nb.t;
+                            bk[rec] = nb.k < 0 ? -1 : (nb.k | (nb.C == 0.0 ? (1 << 30) : 0));
+                            selfk[rec] = hitb.k;
+                            if (decided) ++n_self;
+                            dest = decided ? 1 : 2;
+                        }
+                    }
+                }
+            }
+            const unsigned mS = __ballot_sync(0xffffffffu, dest == 1), mT = __ballot_sync(0xffffffffu, dest == 2),
+                           mF = __ballot_sync(0xffffffffu, dest == 3), mB = __ballot_sync(0xffffffffu, dest == 3 && buf);
+            if (dest == 1) qS[nS + __popc(mS & lt_mask)] = (uint8_t)rec;
+            if (dest == 2) qT[nT + __popc(mT & lt_mask)] = (uint8_t)rec;
+            if (dest == 3) qF[nF + __popc(mF & lt_mask)] = (uint8_t)rec;
+            nS += __popc(mS); nT += __popc(mT); nF += __popc(mF);
+            infl1 -= __popc(mB); infl0 -= __popc(mF) - __popc(mB);
+        } else {
+            // ================= T: BVH traversal bounded by the start sphere's hit
+            const int m = min(nT, 32);
+            const bool active = lane < m;
+            const int rec = active ? (int)qT[nT - m + lane] : 0;
+            nT -= m;
+            if (active) {
+                const double ox = st[0 * kPool + rec], oy = st[1 * kPool + rec], oz = st[2 * kPool + rec];
+                const double dx = st[3 * kPool + rec], dy = st[4 * kPool + rec], dz = st[5 * kPool + rec];
+                const double A = ddot(dx, dy, dz, dx, dy, dz);
+                const int kk = bk[rec];
+                Best best;
+                best.t = bt[rec]; best.k = kk < 0 ? -1 : (kk & 0x3fffffff); best.C = (kk >= 0 && ((kk >> 30) & 1)) ? 0.0 : 1.0;
+                const bool sane = A > 0.0 && A < kInf && (ox * ox + oy * oy + oz * oz) < kCullMaxMag2;
+                bool seq = !(sane && a.tmin >= 0.0);   // such rays take the sequential FP64 scan
+                if (!seq) {
+                    bool deep = false;
+                    bvh_cast(a.sc, ox, oy, oz, dx, dy, dz, A, a.tmin, kInf, best, selfk[rec], n_exact, n_nodes, deep);
+                    seq = deep;   // traversal stack exhausted (degenerate tree) / FP32-denormal direction component
+                }
+                if (seq) {
+                    ++n_ovf;
+                    best = resolve_hits(a.sc, true, 0, nullptr, 0, ox, oy, oz, dx, dy, dz, A, a.tmin, kInf, n_exact);
+                }
+                bt[rec] = best.t;
+                bk[rec] = best.k < 0 ? -1 : (best.k | (best.C == 0.0 ? (1 << 30) : 0));
+                qS[nS + lane] = (uint8_t)rec;
+            }
+            nS += m;
+        }
+    }
+
+    // ---------------- flush counters: warp-shuffle reduce, one atomic per warp and counter
+    uint32_t vals[9] = {n_samples, n_casts, n_exact, n_black, n_early, n_primary, n_ovf, n_nodes, n_self};
+    const int slots[9] = {ST_SAMPLES, ST_CASTS, ST_EXACT_TESTS, ST_BLACK, ST_EARLY_OUTS, ST_PRIMARY_HITS, ST_OVERFLOWS, ST_NODE_TESTS,
+                          ST_SELF_RESOLVED};
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
         unsigned long long v = vals[c];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -397,18 +653,28 @@ struct RayBatchArgs {
     unsigned long long* stats;
 };
 
+// `self`: the sphere the ray starts on (the path's previous hit), -1 for primary / explicit rays.  Only the BVH mode
+// uses it (start-sphere test + tie grid before the traversal, the same device functions as the render kernel).
 __device__ __forceinline__ Best cast_one(const SceneDev& sc, const float4* s_filt, uint16_t* cand, int scan_mode,
-                                         bool alive, double ox, double oy, double oz, double dx, double dy, double dz,
-                                         double A, double tmin, double tmax, uint32_t& n_exact, uint32_t& n_ovf) {
+                                         bool alive, int self, double ox, double oy, double oz, double dx, double dy,
+                                         double dz, double A, double tmin, double tmax, uint32_t& n_exact,
+                                         uint32_t& n_ovf, uint32_t& n_self) {
     if (scan_mode == 2) {  // flattened BVH
         Best best;
         best.t = tmax; best.C = 1.0; best.k = -1;
         if (alive) {
-            const bool ok = A > 0.0 && A < __longlong_as_double(0x7ff0000000000000ll) && tmin >= 0.0;
+            const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+            const bool ok = A > 0.0 && A < kInf && tmin >= 0.0 && (ox * ox + oy * oy + oz * oz) < kCullMaxMag2;
             bool deep = false;
             uint32_t n_nodes = 0;
-            if (ok) best = bvh_cast(sc, ox, oy, oz, dx, dy, dz, A, tmin, tmax, n_exact, n_nodes, deep);
-            if (!ok || deep) { ++n_ovf; best = resolve_hits(sc, true, 0, cand, kThreads, ox, oy, oz, dx, dy, dz, A, tmin, tmax, n_exact); }
+            if (ok) {
+                if (tmax == kInf && self_cast(sc, self, ox, oy, oz, dx, dy, dz, A, tmin, best, n_exact)) { ++n_self; return best; }
+                bvh_cast(sc, ox, oy, oz, dx, dy, dz, A, tmin, tmax, best, self, n_exact, n_nodes, deep);
+            }
+            if (!ok || deep) {
+                ++n_ovf;
+                best = resolve_hits(sc, true, 0, cand, kThreads, ox, oy, oz, dx, dy, dz, A, tmin, tmax, n_exact);
+            }
         }
         return best;
     }
@@ -455,8 +721,9 @@ __global__ void __launch_bounds__(kThreads) hit_kernel(const __grid_constant__ R
             }
         }
         const double A = ddot(dx, dy, dz, dx, dy, dz);
-        const Best best = cast_one(a.sc, s_filt, cand, a.scan_mode, alive, ox, oy, oz, dx, dy, dz, A, a.tmin, a.tmax,
-                                   n_exact, n_ovf);
+        uint32_t n_self = 0;
+        const Best best = cast_one(a.sc, s_filt, cand, a.scan_mode, alive, -1, ox, oy, oz, dx, dy, dz, A, a.tmin, a.tmax,
+                                   n_exact, n_ovf, n_self);
         if (!alive) continue;
         a.idx_out[q] = best.k;
         if (MODE == 1) {
@@ -487,14 +754,14 @@ __global__ void __launch_bounds__(kThreads) ray_color_kernel(const __grid_consta
     const float4* s_filt = reinterpret_cast<const float4*>(smem);
     uint16_t* cand = reinterpret_cast<uint16_t*>(smem + L.cand_off) + threadIdx.x;
     stage_bulk(smem, a.sc.filt, L.filt_bytes, &s_mbar);
-    uint32_t n_exact = 0, n_ovf = 0, n_casts = 0, n_black = 0, n_early = 0, n_primary = 0, n_samples = 0;
+    uint32_t n_exact = 0, n_ovf = 0, n_casts = 0, n_black = 0, n_early = 0, n_primary = 0, n_samples = 0, n_self = 0;
     const int nrounds = (a.nrays + (int)(gridDim.x * blockDim.x) - 1) / (int)(gridDim.x * blockDim.x);
     for (int round = 0; round < nrounds; ++round) {
         const int q = (round * (int)gridDim.x + (int)blockIdx.x) * (int)blockDim.x + (int)threadIdx.x;
         bool alive = q < a.nrays && a.depth >= 0;
         double ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1;
         double cr = 0, cg = 0, cb = 0;
-        int depth = a.depth, bounces = 0;
+        int depth = a.depth, bounces = 0, self = -1;
         uint32_t blk = 1u;
         if (q < a.nrays) {
             ox = a.org[3 * q]; oy = a.org[3 * q + 1]; oz = a.org[3 * q + 2];
@@ -504,8 +771,8 @@ __global__ void __launch_bounds__(kThreads) ray_color_kernel(const __grid_consta
         }
         while (__any_sync(0xffffffffu, alive)) {
             const double A = ddot(dx, dy, dz, dx, dy, dz);
-            const Best best = cast_one(a.sc, s_filt, cand, a.scan_mode, alive, ox, oy, oz, dx, dy, dz, A, a.tmin,
-                                       __longlong_as_double(0x7ff0000000000000ll), n_exact, n_ovf);
+            const Best best = cast_one(a.sc, s_filt, cand, a.scan_mode, alive, self, ox, oy, oz, dx, dy, dz, A, a.tmin,
+                                       __longlong_as_double(0x7ff0000000000000ll), n_exact, n_ovf, n_self);
             if (!alive) continue;
             ++n_casts;
             if (best.k < 0) { sky_color(a.sh, dy, A, bounces, cr, cg, cb); alive = false; continue; }
@@ -519,15 +786,17 @@ __global__ void __launch_bounds__(kThreads) ray_color_kernel(const __grid_consta
             const double tgz = dadd(dadd(rec.pz, rec.nz), rz);
             ox = rec.px; oy = rec.py; oz = rec.pz;
             dx = dsub(tgx, rec.px); dy = dsub(tgy, rec.py); dz = dsub(tgz, rec.pz);
+            self = best.k;
             ++bounces;
             if (--depth < 0) { ++n_black; alive = false; }
         }
         if (q < a.nrays) { a.rgb_out[3 * q] = cr; a.rgb_out[3 * q + 1] = cg; a.rgb_out[3 * q + 2] = cb; }
     }
     if (a.stats) {
-        const uint32_t vals[7] = {n_samples, n_casts, n_exact, n_black, n_early, n_primary, n_ovf};
-        const int slots[7] = {ST_SAMPLES, ST_CASTS, ST_EXACT_TESTS, ST_BLACK, ST_EARLY_OUTS, ST_PRIMARY_HITS, ST_OVERFLOWS};
-        for (int c = 0; c < 7; ++c)
+        const uint32_t vals[8] = {n_samples, n_casts, n_exact, n_black, n_early, n_primary, n_ovf, n_self};
+        const int slots[8] = {ST_SAMPLES, ST_CASTS, ST_EXACT_TESTS, ST_BLACK, ST_EARLY_OUTS, ST_PRIMARY_HITS, ST_OVERFLOWS,
+                              ST_SELF_RESOLVED};
+        for (int c = 0; c < 8; ++c)
             if (vals[c]) atomicAdd(&a.stats[slots[c]], (unsigned long long)vals[c]);
     }
 }

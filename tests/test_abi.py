@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(rt):
 def test_struct_layouts(rt):
     assert C.sizeof(rt.RtCamera) == 96
     assert C.sizeof(rt.RtParams) == 128   # ABI 3: + custom_shading, scatter_mode, albedo, sky_a[3], sky_b[3]
-    assert C.sizeof(rt.RtStats) == 88
+    assert C.sizeof(rt.RtStats) == 96
     assert C.sizeof(rt.RtTileLayout) == 32
 
 

@@ -37,3 +37,14 @@ def test_bvh_builder_invariants(tmp_path):
                     os.path.join(REPO, "tests", "cpp", "bvh_host_test.cc"), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_tie_grid_containment(tmp_path):
+    """rt_bvh.h build_tie_grid on the host: every sphere that can pass the device's FP32 shell test at a point is a
+    giant or listed in the cell the device looks up (ordinary, clustered, nested, coincident and tiny scenes)."""
+    exe = tmp_path / "tie_grid_test"
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-O1", "-std=c++17", "-I", os.path.join(REPO, "petershirleyraytracer_b200", "csrc"),
+                    os.path.join(REPO, "tests", "cpp", "tie_grid_test.cc"), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout[-2000:] + out.stderr[-2000:]
