@@ -4,17 +4,22 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3] [--spp S]
 
 A "step" is one full frame of the workload (BASELINE.json configs[2]: 1200x800 random-spheres scene, 485
-spheres, 500 spp, max depth 50) traced by the CUDA path; for N > 1 the frame's 8x8 tiles are sharded
-round-robin over the ranks, all-gathered with NCCL and de-interleaved (strong scaling).
+spheres, 500 spp, max depth 50) traced by the CUDA path; for N > 1 the frame's 8x8 tiles are dealt to the ranks,
+all-gathered with NCCL and de-interleaved (strong scaling).
 
 One JSON line on stdout (rank 0):
-  value        device-timed throughput, scene resident in HBM, frame left in HBM
+  value        device-timed throughput, scene resident in HBM, frame left in HBM.  Headline = the linear cull-scan
+               kernel BASELINE.json's north_star specifies for this config (RT_SCAN_FILTERED), reference semantics
+               (tmin 0, every cast the reference makes is executed)
   e2e          same metric through the host-buffer C ABI (rt_update_scene + rt_render): H2D of the scene (+ BVH build)
                and D2H of the RGBA frame into pinned memory inside the timed region
   roofline     FP32-FMA roofline of the render kernel: algorithmic work = sphere tests x 11 FP32-pipe
-               instructions, peak = FFMA issue rate measured in this run
+               instructions; peak = FFMA issue rate measured in this run, nominal peak beside it
+  auto_mode    the same frame through the library default (RT_SCAN_AUTO: exact BVH traversal + tie grid)
   cpu_baseline the reference's own CPU code (oracle/_ref) or its C restatement, timed on this host on a
-               bounded sample of the same workload
+               bounded sample of the same workload: all cores, one thread, and (config 1) the reference's own
+               unoptimised build configuration
+  other_configs  short legs of BASELINE configs 1 and 4 (and 5 at 1 and 8 GPUs) with the same keys
 `--impl reference` times that CPU implementation alone (rank 0), all host threads, same metric/config.
 """
 from __future__ import annotations
@@ -33,11 +38,14 @@ sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 
 SLOTS_PER_TEST = 11  # 3 FADD + 2 FMUL + 6 FFMA of programs/sphere.cc:6-14 with A hoisted, r^2 precomputed
+SLOTS_PER_BOX = 14   # one BVH child box: 6 FFMA + 8 min/max/compare
+NOMINAL_FMA_PER_S = 148 * 128 * 1.965e9   # SMs x FP32 lanes x max SM clock (MEASURED_PEAKS.json has no FP32 figure)
+WORKLOAD_KEYS = {"c1": "c1_default", "c3": "c3_book_1200x800", "c4": "c4_bvh_1920x1080", "c5": "c5_book_4k"}
 
 
-def workload(name: str, spp_override: int | None):
+def workload(name: str, spp_override: int | None = None):
     from petershirleyraytracer_b200 import scenes
-    key = {"c1": "c1_default", "c3": "c3_book_1200x800", "c4": "c4_bvh_1920x1080", "c5": "c5_book_4k"}.get(name, name)
+    key = WORKLOAD_KEYS.get(name, name)
     scene_fn, cam_fn, W, H, spp, depth = scenes.CONFIGS[key]
     if spp_override:
         spp = spp_override
@@ -83,19 +91,24 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_rate(wl, target_s: float, threads: int = 0):
-    """Msamples/s of the reference CPU implementation on a bounded sample of the workload: full-width rows
-    from the middle of the frame at the workload's depth; spp and row count sized for ~target_s seconds."""
-    import oracle_lib as ol
-    kind = "reference" if ol.have_ref() else "port"
-    which = "ref" if kind == "reference" else "orc"
-    # all the host cores this process may run on -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1,
-    # which would time the reference on one thread
+def host_cores() -> int:
+    # all the host cores this process may run on -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
     try:
-        avail = len(os.sched_getaffinity(0))
+        return len(os.sched_getaffinity(0))
     except AttributeError:
-        avail = os.cpu_count() or 1
-    cores = avail if threads == 0 else threads
+        return os.cpu_count() or 1
+
+
+def cpu_reference_rate(wl, target_s: float, threads: int = 0, which: str | None = None):
+    """Msamples/s of the reference CPU implementation on a bounded sample of the workload: full-width rows
+    from the middle of the frame at the workload's depth; spp and row count sized for ~target_s seconds.
+    which: "ref" (oracle/_ref/libref.so, -O3), "refO0" (the reference's own unoptimised CMake configuration),
+    "orc" (the C restatement); default: ref if built, else orc."""
+    import oracle_lib as ol
+    if which is None:
+        which = "ref" if ol.have_ref() else "orc"
+    kind = "port" if which == "orc" else "reference"
+    cores = host_cores() if threads == 0 else threads
     cam12 = wl["cam"].as12()
     W, H = wl["W"], wl["H"]
     mid = H // 2
@@ -116,8 +129,17 @@ def cpu_reference_rate(wl, target_s: float, threads: int = 0):
     if dt < 0.6 * target_s and spp < wl["spp"]:   # the probe under-estimated the rate (thread start-up): one longer sample
         spp = int(max(spp + 1, min(wl["spp"], spp * target_s / max(dt, 1e-3))))
         n, dt, (j0, j1) = run(rows, spp)
-    return {"value": n / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": kind,
+    build = {"ref": "-O3 -ffp-contract=off", "refO0": "-O0 (programs/CMakeLists.txt:1-6 sets no flags)", "orc": "-O3 -ffp-contract=off"}[which]
+    return {"value": n / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": kind, "build": build, "seconds": dt,
             "sample": f"rows {j0}..{j1 - 1} of {H} x {W} px x {spp} spp, depth {wl['depth']} ({int(n)} samples, {dt:.1f} s)"}
+
+
+def config_dict(wl, gpus: int):
+    """Identical for the CUDA arm and the reference arm (the driver compares the two dicts)."""
+    return {"workload": f"{wl['name']}: {wl['W']}x{wl['H']} px, {len(wl['radii'])} spheres (book layout, seed 42), "
+                        f"{wl['spp']} spp, max depth {wl['depth']}, tmin 0 (reference semantics)",
+            "width": wl["W"], "height": wl["H"], "spp": wl["spp"], "max_depth": wl["depth"], "spheres": int(len(wl["radii"])),
+            "gpus": gpus}
 
 
 def run_reference_arm(args, wl):
@@ -134,26 +156,169 @@ def run_reference_arm(args, wl):
     v = statistics.mean(x["value"] for x in vals)
     last = vals[-1]
     out = {"impl": "reference", "metric": "Msamples/s", "value": v, "unit": "Msamples/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
-           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": config_dict(wl, args, extra={"note": "reference CPU renderer (unmodified classes, OpenMP over rows); "
-                                                          "each step is a bounded sample of the workload"}),
-           "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+           "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * statistics.mean(x["seconds"] for x in vals),    # measured duration of the bounded sample
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": config_dict(wl, args.gpus),
+           "notes": "reference CPU renderer (unmodified classes, OpenMP over rows); each step is a bounded sample of the workload "
+                    f"sized for ~{per_step:.0f} s",
+           "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"],
+                            "build": last["build"]},
            "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
 
 
-def config_dict(wl, args, extra=None):
-    d = {"workload": f"{wl['name']}: {wl['W']}x{wl['H']} px, {len(wl['radii'])} spheres (book layout, seed 42), "
-                     f"{wl['spp']} spp, max depth {wl['depth']}, tmin 0 (reference semantics)",
-         "width": wl["W"], "height": wl["H"], "spp": wl["spp"], "max_depth": wl["depth"], "spheres": int(len(wl["radii"])),
-         "parallelism": f"tiles8x8 round-robin over {args.gpus} GPU(s)" + (" + NCCL all-gather" if args.gpus > 1 else ""),
-         "l2": "scene (8 KB cull array in the constant bank, 15 KB FP64 array) is cache resident by design; a 256 MB buffer is "
-               "written between timed steps to flush L2"}
-    if extra:
-        d.update(extra)
-    return d
+def load_traffic(wl_name: str, kernel: str):
+    """DRAM bytes per launch of the render kernel from the ncu --set full capture of this workload at HEAD
+    (profiles/r2_traffic.json, written from the committed ncu summaries); None if there is no capture for it."""
+    path = os.path.join(REPO, "profiles", "r2_traffic.json")
+    try:
+        return json.load(open(path)).get(wl_name, {}).get(kernel)
+    except Exception:
+        return None
+
+
+class GpuBench:
+    """One workload on this rank's GPU: device-timed legs and the host-buffer e2e leg."""
+
+    def __init__(self, wl, rt, torch, dist, world, rank, local):
+        self.wl, self.rt, self.torch, self.dist = wl, rt, torch, dist
+        self.world, self.rank, self.local = world, rank, local
+        self.dev = torch.device("cuda", local)
+        self.W, self.H, self.spp, self.depth = wl["W"], wl["H"], wl["spp"], wl["depth"]
+        self.cam = wl["cam"]
+        self.scene = rt.Scene(wl["centres"], wl["radii"], device=local)
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.frame = torch.empty(self.H * self.W * 4, dtype=torch.uint8, device=self.dev)
+        layout = rt.tile_layout(self.params(rt.SCAN_AUTO, False))
+        self.shard = torch.empty(layout.shard_bytes, dtype=torch.uint8, device=self.dev) if world > 1 else None
+        self.gathered = torch.empty(world * layout.shard_bytes, dtype=torch.uint8, device=self.dev) if world > 1 else None
+        self.samples_per_step = self.W * self.H * self.spp
+        self.big = len(wl["radii"]) > 4080   # beyond the linear scan's constant bank: BVH only
+
+    def params(self, scan_mode, early_out, spp=None):
+        return self.rt.make_params(self.W, self.H, spp or self.spp, self.depth, seed=0, early_out=early_out, scan_mode=scan_mode,
+                                   shard_rank=self.rank, shard_count=self.world)
+
+    def step(self, p, scene=None):
+        """One frame, device buffers only.  Returns the kernels launched."""
+        rt, sc = self.rt, scene or self.scene
+        if self.world == 1:
+            rt.render_device(sc, self.cam, p, self.frame.data_ptr(), 0, self.stream)
+            return 1
+        rt.render_device(sc, self.cam, p, self.shard.data_ptr(), 0, self.stream)
+        self.dist.all_gather_into_tensor(self.gathered, self.shard)
+        rt.deinterleave(p, self.gathered.data_ptr(), self.frame.data_ptr(), self.local, self.stream)
+        return 2
+
+    def timed(self, p, nsteps, nwarm, flush, sampler=None, warm_p=None):
+        torch, dist, rt = self.torch, self.dist, self.rt
+        for _ in range(nwarm):
+            self.step(warm_p or p); rt.render_finish(self.scene)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        if sampler:
+            sampler.start()
+        tot_ms, kern_ms, launches, stats = 0.0, 0.0, 0, None
+        for _ in range(nsteps):
+            flush.fill_(1)  # L2 flush between timed iterations (outside the timed region)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            launches += self.step(p)
+            e1.record()
+            e1.synchronize()
+            stats = rt.render_finish(self.scene)
+            tot_ms += e0.elapsed_time(e1)
+            kern_ms += stats["kernel_ms"]
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        t = torch.tensor([tot_ms, kern_ms], dtype=torch.float64, device=self.dev)
+        cnt = torch.tensor([stats["sphere_tests"], stats["node_tests"], stats["exact_tests"], stats["casts"], stats["samples"],
+                            stats["self_resolved"]], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt)
+        keys = ("sphere_tests", "node_tests", "exact_tests", "casts", "samples", "self_resolved")
+        return {"ms": t[0].item(), "kernel_ms": t[1].item(), "launches": launches, "steps": nsteps,
+                "value": self.samples_per_step * nsteps / (t[0].item() * 1e-3) / 1e6,
+                "counts": dict(zip(keys, (x.item() for x in cnt)))}     # whole-job sums of the last step
+
+    def e2e(self, p, nsteps, nwarm=2):
+        """Host buffers through the public C ABI: every step re-uploads the flattened hittable_list into one reused device
+        scene (rt_update_scene with a full rebuild: H2D of the sphere arrays + BVH / tie-grid build; no cudaMalloc /
+        cudaFree, whose latency on shared hosts is erratic) and reads the frame back into pinned memory."""
+        torch, dist, rt, wl = self.torch, self.dist, self.rt, self.wl
+        if not hasattr(self, "e2e_scene"):
+            self.e2e_scene = rt.Scene(wl["centres"], wl["radii"], device=self.local)
+            self.host_frame = torch.empty(self.H * self.W * 4, dtype=torch.uint8).pin_memory()
+            self.host_view = self.host_frame.numpy().reshape(self.H, self.W, 4)
+        sc = self.e2e_scene
+
+        def one():
+            sc.update(wl["centres"], wl["radii"], refit=False)
+            if self.world == 1:
+                rt.render(sc, self.cam, p, out=self.host_view)
+            else:
+                self.step(p, scene=sc)
+                if self.rank == 0:
+                    self.host_frame.copy_(self.frame, non_blocking=False)
+                rt.render_finish(sc)
+
+        for _ in range(nwarm):
+            one()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        per_step = []
+        for _ in range(nsteps):
+            ts = time.perf_counter()
+            one()
+            per_step.append(round(1e3 * (time.perf_counter() - ts), 1))
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(s, op=dist.ReduceOp.MAX)
+        h2d = wl["centres"].nbytes + wl["radii"].nbytes + 96 + 128      # sphere arrays + camera + params
+        return {"value": self.samples_per_step * nsteps / s.item() / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(self.H * self.W * 4), "ms_per_step_rank0": per_step}
+
+    def roofline(self, leg, fma_per_s, mode_name):
+        """FP32 roofline of one device-timed leg on EXECUTED work (so it can never exceed 1)."""
+        c = leg["counts"]
+        if mode_name == "scan":
+            slots = c["sphere_tests"] * SLOTS_PER_TEST
+        else:
+            slots = c["node_tests"] * SLOTS_PER_BOX + c["exact_tests"] * SLOTS_PER_TEST
+        kernel_s = leg["kernel_ms"] * 1e-3 / leg["steps"]              # average launch duration of the render kernel
+        achieved = slots / self.world * 2 / kernel_s / 1e12             # counts are whole-job sums; ranks run concurrently
+        peak, nominal = fma_per_s * 2 / 1e12, NOMINAL_FMA_PER_S * 2 / 1e12
+        return {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_nominal": nominal, "frac_nominal": achieved / nominal,
+                "kernel_ms_per_step": leg["kernel_ms"] / leg["steps"],
+                "casts_per_sample": c["casts"] / max(c["samples"], 1),
+                "sphere_tests_per_step": c["sphere_tests"], "box_tests_per_step": c["node_tests"],
+                "fp64_sphere_tests_per_step": c["exact_tests"]}
+
+    def close(self):
+        if hasattr(self, "e2e_scene"):
+            self.e2e_scene.close()
+        self.scene.close()
+
+
+def l2_note(wl, big):
+    n = len(wl["radii"])
+    if big:
+        return (f"scene = {n * 32 / 1e6:.1f} MB FP64 sphere array + ~{n * 46 / 1e6:.1f} MB BVH / tie grid: L2 resident (126 MB), not L1; "
+                "a 256 MB buffer is written between timed steps to flush L2")
+    return (f"scene ({(n + 20) * 16 / 1e3:.0f} KB cull array in the constant bank, {n * 32 / 1e3:.0f} KB FP64 array) is cache resident by "
+            "design; a 256 MB buffer is written between timed steps to flush L2")
 
 
 def main():
@@ -165,6 +330,7 @@ def main():
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--spp", type=int, default=None, help="override the workload's spp (quick checks; not the contract config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     wl = workload(args.workload, args.spp)
 
@@ -172,7 +338,6 @@ def main():
         run_reference_arm(args, wl)
         return
 
-    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -186,193 +351,102 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     rt.lib()  # fail loudly if the CUDA library is missing
-
-    W, H, spp, depth = wl["W"], wl["H"], wl["spp"], wl["depth"]
-    cam = wl["cam"]
-    scene = rt.Scene(wl["centres"], wl["radii"], device=local)
-    stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    frame = torch.empty(H * W * 4, dtype=torch.uint8, device=dev)
+    fma_per_s, _ = rt.measure_fp32_peak(local)
 
-    # scenes beyond the linear scan's 4080 spheres (BASELINE config 4) are benchmarked through the BVH; their roofline
-    # counts the executed box tests (14 FP32-pipe slots each: 6 FFMA + 8 min/max/compare) and sphere tests (11)
-    big = len(wl["radii"]) > 4080
-    SLOTS_PER_BOX = 14
-
-    def make(early_out, scan_mode=None):
-        if scan_mode is None:
-            scan_mode = rt.SCAN_BVH if big else rt.SCAN_FILTERED
-        # headline = the linear cull-scan kernel BASELINE.json's north_star specifies for this config (its metric,
-        # % of the FP32-FMA roofline, is defined on the scan); the library's default AUTO mode (exact BVH
-        # traversal) is timed too, device-side and end to end, and reported as "auto_mode"
-        return rt.make_params(W, H, spp, depth, seed=0, early_out=early_out, scan_mode=scan_mode, shard_rank=rank,
-                              shard_count=world)
-
-    layout = rt.tile_layout(make(False))
-    shard = torch.empty(layout.shard_bytes, dtype=torch.uint8, device=dev) if world > 1 else None
-    gathered = torch.empty(world * layout.shard_bytes, dtype=torch.uint8, device=dev) if world > 1 else None
-
-    def step(p):
-        """One frame, device buffers only.  Returns the kernels launched."""
-        if world == 1:
-            rt.render_device(scene, cam, p, frame.data_ptr(), 0, stream)
-            return 1
-        rt.render_device(scene, cam, p, shard.data_ptr(), 0, stream)
-        dist.all_gather_into_tensor(gathered, shard)
-        rt.deinterleave(p, gathered.data_ptr(), frame.data_ptr(), local, stream)
-        return 2
-
-    def timed(p, nsteps, nwarm, sampler=None):
-        for _ in range(nwarm):
-            step(p); rt.render_finish(scene)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        if sampler:
-            sampler.start()
-        tot_ms, kern_ms, launches, stats = 0.0, 0.0, 0, None
-        for _ in range(nsteps):
-            flush.fill_(1)  # L2 flush between timed iterations (outside the timed region)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            launches += step(p)
-            e1.record()
-            e1.synchronize()
-            stats = rt.render_finish(scene)
-            tot_ms += e0.elapsed_time(e1)
-            kern_ms += stats["kernel_ms"]
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t = torch.tensor([tot_ms, kern_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t[0].item(), t[1].item(), launches, stats
+    b = GpuBench(wl, rt, torch, dist, world, rank, local)
+    head_mode = rt.SCAN_BVH if b.big else rt.SCAN_FILTERED
+    head_name = "bvh" if b.big else "scan"
 
     # ---- headline: reference semantics, every cast executed
     sampler = ClockSampler(local) if rank == 0 else None
-    tot_ms, kern_ms, launches, stats = timed(make(False), args.steps, args.warmup, sampler)
+    head = b.timed(b.params(head_mode, False), args.steps, args.warmup, flush, sampler)
     clocks = sampler.stop() if sampler else None
-    samples_per_step = W * H * spp
-    value = samples_per_step * args.steps / (tot_ms * 1e-3) / 1e6
-
-    # per-rank counters -> whole-job sums for the roofline
-    slots = (stats["node_tests"] * SLOTS_PER_BOX + stats["exact_tests"] * SLOTS_PER_TEST) if big else stats["sphere_tests"] * SLOTS_PER_TEST
-    cnt = torch.tensor([slots / SLOTS_PER_TEST, stats["casts"], stats["samples"], stats["exact_tests"]], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(cnt)
-    tests_per_step, casts_per_step = cnt[0].item(), cnt[1].item()
-
+    k = max(1, min(args.steps, 3))
     # ---- same frame with the exact early-out (bit-identical image, fewer casts)
-    eo_ms, eo_kern_ms, _, eo_stats = timed(make(True), max(1, args.steps), 1)
-    value_eo = samples_per_step * max(1, args.steps) / (eo_ms * 1e-3) / 1e6
+    eo = b.timed(b.params(head_mode, True), k, 1, flush)
+    # ---- the library's AUTO mode on the same frame (exact BVH traversal + tie grid for this scene size)
+    auto = b.timed(b.params(rt.SCAN_AUTO, False), k, 1, flush)
+    auto_eo = b.timed(b.params(rt.SCAN_AUTO, True), k, 1, flush)
+    # ---- e2e: host buffers through the public C ABI
+    e2e = b.e2e(b.params(head_mode, False), args.steps)
+    e2e_auto = b.e2e(b.params(rt.SCAN_AUTO, False), k)
 
-    # ---- the library's AUTO mode on the same frame (exact BVH traversal for this scene size)
-    auto_ms, _, _, auto_stats = timed(make(False, rt.SCAN_AUTO), max(1, args.steps), 1)
-    value_auto = samples_per_step * max(1, args.steps) / (auto_ms * 1e-3) / 1e6
-
-    # ---- e2e: host buffers through the public C ABI (upload scene, render, read the frame back)
-    e2e = None
-    h2d = wl["centres"].nbytes + wl["radii"].nbytes + 96 + 64
-    d2h = H * W * 4
-    host_frame = torch.empty(H * W * 4, dtype=torch.uint8).pin_memory()
-    host_view = host_frame.numpy().reshape(H, W, 4)
-
-    # One device scene for all e2e steps: every step re-uploads the flattened hittable_list into it (rt_update_scene
-    # with a full rebuild: H2D of the sphere arrays + BVH build, no cudaMalloc / cudaFree, whose latency on shared
-    # hosts is erratic -- 100-600 ms stalls were seen inside cudaFree) and reads the frame back into pinned memory.
-    e2e_scene = rt.Scene(wl["centres"], wl["radii"], device=local)
-
-    def e2e_step(p):
-        t_a = time.perf_counter()
-        sc = e2e_scene
-        sc.update(wl["centres"], wl["radii"], refit=False)           # H2D of the flattened hittable_list + BVH rebuild
-        t_b = time.perf_counter()
-        if world == 1:
-            rgba, _, st = rt.render(sc, cam, p, out=host_view)        # kernel + D2H into the pinned host frame
-            if os.environ.get("RT_BENCH_DEBUG"):
-                print(f"[e2e] upload {1e3 * (t_b - t_a):.1f} ms, render call {1e3 * (time.perf_counter() - t_b):.1f} ms "
-                      f"(kernel {st['kernel_ms']:.1f} ms)", file=sys.stderr)
-        else:
-            rt.render_device(sc, cam, p, shard.data_ptr(), 0, stream)
-            dist.all_gather_into_tensor(gathered, shard)
-            rt.deinterleave(p, gathered.data_ptr(), frame.data_ptr(), local, stream)
-            if rank == 0:
-                host_frame.copy_(frame, non_blocking=False)
-            rt.render_finish(sc)
-
-    def e2e_rate(p):
-        for _ in range(2):  # untimed: first-use allocator / module initialisation
-            e2e_step(p)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        per_step = []
-        for _ in range(args.steps):
-            ts = time.perf_counter()
-            e2e_step(p)
-            per_step.append(1e3 * (time.perf_counter() - ts))
-            if os.environ.get("RT_BENCH_DEBUG"):
-                print(f"[e2e] step {per_step[-1]:.1f} ms", file=sys.stderr)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-        # value: all K steps over the whole wall time (max over ranks); the per-step list (rank 0) shows host hiccups
-        return samples_per_step * args.steps / e2e_s.item() / 1e6, [round(x, 1) for x in per_step]
-
-    e2e_v, e2e_steps = e2e_rate(make(False))
-    e2e = {"value": e2e_v, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "ms_per_step_rank0": e2e_steps}
-    e2e_auto, e2e_auto_steps = e2e_rate(make(False, rt.SCAN_AUTO))
+    # ---- short legs of the other BASELINE configs (device-timed value, e2e, executed-work roofline)
+    other = {}
+    if not args.no_other_configs and args.workload == "c3" and not args.spp:
+        names = ["c1", "c4"] if world == 1 else []
+        if world in (1, 8):
+            names.append("c5")
+        for name in names:
+            owl = workload(name)
+            ob = GpuBench(owl, rt, torch, dist, world, rank, local)
+            mode = rt.SCAN_BVH if ob.big else rt.SCAN_FILTERED
+            nst = 1 if name == "c5" else 2
+            warm = ob.params(mode, False, spp=max(1, owl["spp"] // 64))      # (a short frame warms caches / clocks; the timed steps are full frames)
+            leg = ob.timed(ob.params(mode, False), nst, 1, flush, warm_p=warm)
+            entry = {"config": config_dict(owl, world), "scan_mode": "bvh" if ob.big else "linear cull scan",
+                     "value": leg["value"], "unit": "Msamples/s", "steps": nst, "ms_per_step": leg["ms"] / nst,
+                     "roofline": ob.roofline(leg, fma_per_s, "bvh" if ob.big else "scan")}
+            if name != "c5":
+                entry["e2e"] = ob.e2e(ob.params(mode, False), nst, nwarm=1)
+                if not ob.big:
+                    aleg = ob.timed(ob.params(rt.SCAN_AUTO, False), nst, 1, flush)
+                    entry["auto_mode"] = {"value": aleg["value"], "roofline": ob.roofline(aleg, fma_per_s, "bvh"),
+                                          "self_resolved_per_cast": aleg["counts"]["self_resolved"] / max(aleg["counts"]["casts"], 1)}
+            else:
+                aleg = ob.timed(ob.params(rt.SCAN_AUTO, False), nst, 0, flush)
+                entry["auto_mode"] = {"value": aleg["value"]}
+            other[name] = entry
+            ob.close()
 
     if rank == 0:
-        fma_per_s, _ = rt.measure_fp32_peak(local)
-        kernel_s = kern_ms * 1e-3 / args.steps                       # average launch duration of the render kernel
-        # tests are whole-job sums; with N ranks the kernels run concurrently, so per-GPU achieved = sum / N
-        achieved = tests_per_step / world * SLOTS_PER_TEST * 2 / kernel_s / 1e12
-        peak = fma_per_s * 2 / 1e12
-        traffic = None
-        tpath = os.path.join(REPO, "profiles", "render_kernel_traffic.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": traffic,
-                    "note": "FP32-FMA roofline (no tensor cores, HBM traffic ~nil): achieved = sphere tests x 11 FP32-pipe "
-                            "instructions x 2 flop / render-kernel time (CUDA events, avg over the timed launches, per GPU); "
-                            "peak = FFMA rate measured in this run by rt_measure_fp32_peak (MEASURED_PEAKS.json has no FP32 "
-                            f"figure; nominal 148 SMs x 128 lanes x 1.965 GHz x 2 = 74.4); the kernel itself issues "
-                            "7 FMA-pipe + ~1.9 other instructions per test in the scan loop",
-                    "sphere_tests_per_step": tests_per_step,   # (BVH workloads: executed box + sphere test slots / 11) "casts_per_sample": casts_per_step / samples_per_step,
-                    "kernel_ms_per_step": kern_ms / args.steps,
-                    "with_early_out": {"msamples_s": value_eo, "casts_per_sample": None if eo_stats is None else
-                                       eo_stats["casts"] * world / samples_per_step}}
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline and not big:   # (the reference's O(N) scan of 1e5 spheres: ~1 ms per cast)
+        roofline = b.roofline(head, fma_per_s, head_name)
+        kern = "render_wave_kernel" if b.big else "render_kernel<2,1>"
+        roofline["traffic"] = load_traffic(wl["name"], kern)
+        roofline["note"] = ("FP32-FMA roofline (no tensor cores, HBM traffic ~nil): achieved = executed sphere tests x 11 FP32-pipe "
+                            "instructions (+ BVH box tests x 14) x 2 flop / render-kernel time (CUDA events on the launching stream, "
+                            "avg over the timed launches, per GPU); peak = FFMA rate measured in this run by rt_measure_fp32_peak, "
+                            "peak_nominal = 148 SMs x 128 lanes x 1.965 GHz x 2 (MEASURED_PEAKS.json has no FP32 figure); the scan "
+                            "loop itself issues 7 FMA-pipe + ~1.9 other instructions per test")
+        roofline["with_early_out"] = {"msamples_s": eo["value"], "casts_per_sample": eo["counts"]["casts"] / max(eo["counts"]["samples"], 1)}
+        cpu = cpu1 = cpu_own = None
+        if world == 1 and not args.no_cpu_baseline and not b.big:   # (the reference's O(N) scan of 1e5 spheres: ~1 ms per cast)
             cpu = cpu_reference_rate(wl, 12.0)
-        out = {"metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            cpu1 = cpu_reference_rate(wl, 8.0, threads=1)             # the reference itself is single-threaded (programs/main.cc:51-92)
+            try:
+                import oracle_lib as ol
+                if ol.have_ref_O0():                                  # its own build configuration, on its own scene (config 1)
+                    c1 = workload("c1")
+                    cpu_own = {"O0_1thread": cpu_reference_rate(c1, 6.0, threads=1, which="refO0"),
+                               "O3_1thread": cpu_reference_rate(c1, 4.0, threads=1, which="ref"),
+                               "workload": config_dict(c1, 0)["workload"]}
+            except Exception as e:  # noqa: BLE001
+                cpu_own = {"error": repr(e)}
+        ca = auto["counts"]
+        out = {"metric": "Msamples/s", "value": head["value"], "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": head["ms"] / args.steps, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "f64 hit/shading + f32 cull", "data": "synthetic",
-               "config": config_dict(wl, args, extra={"early_out": False, "paths_per_lane": 1 if big else 2,
-                                                      "scan_mode": "4-wide BVH (RT_SCAN_BVH)" if big else "linear cull scan (RT_SCAN_FILTERED)",
-                                                      "value_with_exact_early_out": value_eo}),
-               "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+               "config": config_dict(wl, world),
+               "notes": {"scan_mode": "4-wide BVH + tie grid (RT_SCAN_BVH)" if b.big else "linear cull scan (RT_SCAN_FILTERED)",
+                         "early_out": False, "paths_per_lane": 1 if b.big else 2,
+                         "parallelism": f"tiles8x8 dealt to {world} GPU(s)" + (" + NCCL all-gather" if world > 1 else ""),
+                         "l2": l2_note(wl, b.big), "value_with_exact_early_out": eo["value"]},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": head["launches"], "roofline": roofline,
+               "cpu_baseline": cpu, "cpu_baseline_1thread": cpu1, "cpu_baseline_reference_build": cpu_own,
                # the same frame, same semantics, through the library's DEFAULT scan mode (RT_SCAN_AUTO -> exact BVH
-               # traversal, SAH build at upload): what a caller of rt_render gets without asking for anything
-               "auto_mode": {"scan_mode": "RT_SCAN_AUTO (flattened BVH, exact closest-hit semantics)", "value": value_auto,
-                             "e2e": e2e_auto, "e2e_ms_per_step_rank0": e2e_auto_steps, "unit": "Msamples/s",
-                             "box_tests_per_cast": None if not auto_stats else auto_stats["node_tests"] / max(1, auto_stats["casts"]),
-                             "fp64_sphere_tests_per_cast": None if not auto_stats else auto_stats["exact_tests"] / max(1, auto_stats["casts"])}}
+               # traversal, SAH build + tie grid at upload): what a caller of rt_render gets without asking for anything
+               "auto_mode": {"scan_mode": "RT_SCAN_AUTO (flattened BVH + start-sphere test / tie grid, exact closest-hit semantics)",
+                             "value": auto["value"], "value_with_exact_early_out": auto_eo["value"],
+                             "e2e": e2e_auto["value"], "e2e_ms_per_step_rank0": e2e_auto["ms_per_step_rank0"], "unit": "Msamples/s",
+                             "kernel_ms_per_step": auto["kernel_ms"] / auto["steps"],
+                             "roofline_executed_work": b.roofline(auto, fma_per_s, "bvh"),
+                             "box_tests_per_cast": ca["node_tests"] / max(ca["casts"], 1),
+                             "fp64_sphere_tests_per_cast": ca["exact_tests"] / max(ca["casts"], 1),
+                             "casts_decided_without_traversal": ca["self_resolved"] / max(ca["casts"], 1)},
+               "other_configs": other}
         print(json.dumps(out), flush=True)
-    e2e_scene.close()
-    scene.close()
+    b.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -168,6 +168,33 @@ int rt_render_pass(const rt_scene* scene, const rt_camera* cam, const rt_params*
 int rt_render_pass_device(const rt_scene* scene, const rt_camera* cam, const rt_params* params, int32_t sample_begin,
                           void* d_accum, void* d_rgba /* may be NULL */, void* stream);
 
+/* Device-resident progressive accumulator: the same sums as rt_render_pass, kept on the GPU between passes -- no
+ * allocation and no host copy per pass (a 64-pass render costs what one render costs).  rt_accum_add traces the next
+ * params->spp samples of every pixel ([samples so far, + spp); params->width/height must match) and is asynchronous
+ * unless stats_out is given; rt_accum_frame waits and copies write_color over all samples so far; rt_accum_read /
+ * rt_accum_write move the raw W*H*3 uint64 sums (checkpoint / resume, also across devices). */
+typedef struct rt_accum rt_accum;
+int rt_accum_create(int32_t width, int32_t height, int32_t device, rt_accum** out);
+void rt_accum_destroy(rt_accum* accum);
+int rt_accum_samples(const rt_accum* accum);
+int rt_accum_reset(rt_accum* accum);
+int rt_accum_add(const rt_scene* scene, const rt_camera* cam, const rt_params* params, rt_accum* accum, rt_stats* stats_out);
+int rt_accum_frame(const rt_accum* accum, uint8_t* rgba_out);
+int rt_accum_read(const rt_accum* accum, uint64_t* sums_out);
+int rt_accum_write(rt_accum* accum, const uint64_t* sums, int32_t samples_done);
+/* write_color over a frame-ordered device accumulator (W*H*3 uint64) holding total_samples samples per pixel -> d_rgba.
+ * Last step of a render whose samples were split over ranks and whose sums were added up with an integer all-reduce. */
+int rt_accum_to_frame(const rt_params* params, const void* d_accum, int32_t total_samples, void* d_rgba, int32_t device,
+                      void* stream);
+
+/* rt_render on several GPUs of this process: scenes[i] holds the same spheres on device i (one rt_upload_scene per
+ * device); the frame's 8x8 tiles are dealt to the scenes (tile t -> scene t % n_scenes), all shards render
+ * concurrently, and every device stores its pixels straight into the first device's frame over NVLink peer access
+ * (no gather step; without peer access the shards come back through the host).  Same frame, bit for bit, as
+ * rt_render on one device.  params->shard_count must be 1.  stats_out: counters summed, kernel_ms = the slowest shard. */
+int rt_render_multi(rt_scene* const* scenes, int32_t n_scenes, const rt_camera* cam, const rt_params* params,
+                    uint8_t* rgba_out, rt_stats* stats_out);
+
 int rt_get_tile_layout(const rt_params* params, rt_tile_layout* out);
 /* d_gathered: shard_count consecutive shard buffers (all-gather output) -> d_rgba frame. */
 int rt_deinterleave(const rt_params* params, const void* d_gathered, void* d_rgba, int32_t device, void* stream);

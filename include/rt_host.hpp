@@ -299,6 +299,27 @@ private:
     rt_scene* scene_ = nullptr;
 };
 
+// The same world on several GPUs of this process (one device_world per device): rt::render deals the frame's tiles to
+// them and every GPU stores its pixels into the first one's frame over NVLink (rt_render_multi).
+class device_world_group {
+public:
+    device_world_group(const hittable& world, const std::vector<int>& devices) {
+        if (devices.empty()) throw error(RT_ERR_INVALID, "device_world_group needs at least one device");
+        for (int d : devices) worlds_.push_back(std::make_unique<device_world>(world, d));
+    }
+    int devices() const { return (int)worlds_.size(); }
+    const device_world& operator[](int i) const { return *worlds_[(size_t)i]; }
+    void update(const hittable& world, bool refit = true) { for (auto& w : worlds_) w->update(world, refit); }
+    std::vector<rt_scene*> handles() const {
+        std::vector<rt_scene*> h;
+        for (const auto& w : worlds_) h.push_back(const_cast<rt_scene*>(w->handle()));
+        return h;
+    }
+
+private:
+    std::vector<std::unique_ptr<device_world>> worlds_;
+};
+
 struct frame {
     int width = 0, height = 0;
     std::vector<uint8_t> rgba;  // row 0 = top row, the order main() prints
@@ -335,6 +356,21 @@ inline frame render(const hittable& world, const camera& cam, int width, int hei
     device_world dw(world, device);
     return render(dw, cam, default_params(width, height, spp, max_depth, seed));
 }
+// The same loop over several GPUs (tiles dealt to the devices; the frame is the single-GPU frame bit for bit).
+inline frame render(const device_world_group& worlds, const camera& cam, const rt_params& p) {
+    frame f;
+    f.width = p.width; f.height = p.height;
+    f.rgba.resize((size_t)p.width * p.height * 4);
+    const rt_camera c = to_abi(cam);
+    const std::vector<rt_scene*> h = worlds.handles();
+    check(rt_render_multi(h.data(), (int32_t)h.size(), &c, &p, f.rgba.data(), &f.stats));
+    return f;
+}
+inline frame render(const hittable& world, const camera& cam, int width, int height, int spp, int max_depth,
+                    uint64_t seed, const std::vector<int>& devices) {
+    device_world_group g(world, devices);
+    return render(g, cam, default_params(width, height, spp, max_depth, seed));
+}
 
 // Progressive / resumable form of the same loop (where the reference can only report "Scanline remaining",
 // programs/main.cc:74): add(n) traces the next n samples of every pixel and folds them into integer sums, so
@@ -342,33 +378,50 @@ inline frame render(const hittable& world, const camera& cam, int width, int hei
 // sums() / resume() let a caller checkpoint the accumulator and continue later (or on another GPU).
 class progressive_render {
 public:
-    progressive_render(const device_world& world, const camera& cam, const rt_params& p)
-        : world_(world), cam_(to_abi(cam)), p_(p), accum_((size_t)p.width * p.height * 3, 0) {
+    progressive_render(const device_world& world, const camera& cam, const rt_params& p, int device = 0)
+        : world_(world), cam_(to_abi(cam)), p_(p) {
         frame_.width = p.width; frame_.height = p.height;
         frame_.rgba.resize((size_t)p.width * p.height * 4);
+        check(rt_accum_create(p.width, p.height, device, &accum_));
     }
-    const frame& add(int samples) {
+    ~progressive_render() { rt_accum_destroy(accum_); }
+    progressive_render(const progressive_render&) = delete;
+    progressive_render& operator=(const progressive_render&) = delete;
+    // Traces the next `samples` samples of every pixel into the device-resident sums (rt_accum_add: no allocation and no
+    // host copy per pass; asynchronous).  current() fetches the frame when somebody wants to look at it.
+    void add(int samples) {
         rt_params q = p_;
         q.spp = samples;
-        check(rt_render_pass(world_.handle(), &cam_, &q, done_, accum_.data(), frame_.rgba.data(), &frame_.stats));
-        done_ += samples;
+        check(rt_accum_add(world_.handle(), &cam_, &q, accum_, nullptr));
+        fresh_ = false;
+    }
+    int samples_done() const { return rt_accum_samples(accum_); }
+    const frame& current() {
+        if (!fresh_) {
+            check(rt_accum_frame(accum_, frame_.rgba.data()));
+            check(rt_render_finish(world_.handle(), &frame_.stats));   // counters of the last pass
+            fresh_ = true;
+        }
         return frame_;
     }
-    int samples_done() const { return done_; }
-    const frame& current() const { return frame_; }
-    const std::vector<uint64_t>& sums() const { return accum_; }  // 20.44 fixed point, W*H*3, row 0 = top
+    std::vector<uint64_t> sums() const {  // 20.44 fixed point, W*H*3, row 0 = top: the checkpoint
+        std::vector<uint64_t> s((size_t)p_.width * p_.height * 3);
+        check(rt_accum_read(accum_, s.data()));
+        return s;
+    }
     void resume(const std::vector<uint64_t>& sums, int samples_done) {
-        if (sums.size() != accum_.size() || samples_done < 0) throw error(RT_ERR_INVALID, "checkpoint does not match this frame");
-        accum_ = sums; done_ = samples_done;
+        if (sums.size() != (size_t)p_.width * p_.height * 3 || samples_done < 0) throw error(RT_ERR_INVALID, "checkpoint does not match this frame");
+        check(rt_accum_write(accum_, sums.data(), samples_done));
+        fresh_ = false;
     }
 
 private:
     const device_world& world_;
     rt_camera cam_;
     rt_params p_;
-    std::vector<uint64_t> accum_;
+    rt_accum* accum_ = nullptr;
     frame frame_;
-    int done_ = 0;
+    bool fresh_ = false;
 };
 
 // programs/main.cc:70 + the per-pixel lines write_color emits (programs/color.h:21-23), from the 8-bit frame.

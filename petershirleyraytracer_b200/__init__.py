@@ -27,7 +27,8 @@ ABI_SYMBOLS = [
     "rt_render_device", "rt_render_finish", "rt_get_tile_layout", "rt_deinterleave", "rt_primary_hits", "rt_hit",
     "rt_ray_color", "rt_write_color", "rt_get_ray", "rt_philox", "rt_measure_fp32_peak", "rt_device_info",
     "rt_check_division", "rt_update_scene", "rt_accum_bytes", "rt_render_pass", "rt_render_pass_device",
-    "rt_params_init", "rt_ray_color_params",
+    "rt_params_init", "rt_ray_color_params", "rt_accum_create", "rt_accum_destroy", "rt_accum_samples", "rt_accum_reset",
+    "rt_accum_add", "rt_accum_frame", "rt_accum_read", "rt_accum_write", "rt_accum_to_frame", "rt_render_multi",
 ]
 
 
@@ -105,6 +106,18 @@ def lib() -> C.CDLL:
     L.rt_check_division.argtypes = [C.c_int32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
     L.rt_params_init.argtypes = [C.POINTER(RtParams), C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     L.rt_ray_color_params.argtypes = [vp, dp, dp, C.c_int32, C.POINTER(RtParams), dp, C.POINTER(RtStats)]
+    L.rt_accum_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.rt_accum_destroy.argtypes = [vp]
+    L.rt_accum_destroy.restype = None
+    L.rt_accum_samples.argtypes = [vp]
+    L.rt_accum_reset.argtypes = [vp]
+    L.rt_accum_add.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtParams), vp, C.POINTER(RtStats)]
+    L.rt_accum_frame.argtypes = [vp, C.POINTER(C.c_uint8)]
+    L.rt_accum_read.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.rt_accum_write.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int32]
+    L.rt_accum_to_frame.argtypes = [C.POINTER(RtParams), vp, C.c_int32, vp, C.c_int32, vp]
+    L.rt_render_multi.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(RtCamera), C.POINTER(RtParams), C.POINTER(C.c_uint8),
+                                  C.POINTER(RtStats)]
     if L.rt_abi_version() != ABI_VERSION:
         raise RtError(f"{LIB_PATH} has ABI {L.rt_abi_version()}, this binding needs {ABI_VERSION}: rebuild the library")
     _lib = L
@@ -284,6 +297,79 @@ def render_pass(scene: Scene, cam: Camera, params: RtParams, sample_begin: int, 
                                 accum.ctypes.data_as(C.POINTER(C.c_uint64)),
                                 rgba.ctypes.data_as(C.POINTER(C.c_uint8)) if want_rgba else None, C.byref(st)))
     return accum, rgba, st.as_dict()
+
+
+class Accumulator:
+    """rt_accum: device-resident progressive accumulator (fixed-point radiance sums + the frame of all samples so far)."""
+
+    def __init__(self, width: int, height: int, device: int = 0):
+        self.width, self.height, self.device = width, height, device
+        self._h = C.c_void_p()
+        _check(lib().rt_accum_create(width, height, device, C.byref(self._h)))
+
+    @property
+    def samples(self) -> int:
+        return lib().rt_accum_samples(self._h)
+
+    def add(self, scene: Scene, cam: Camera, params: RtParams, want_stats: bool = False):
+        """Traces the next params.spp samples of every pixel; asynchronous unless want_stats."""
+        st = RtStats()
+        cs = cam.c_struct()
+        _check(lib().rt_accum_add(scene.handle, C.byref(cs), C.byref(params), self._h, C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
+    def frame(self) -> np.ndarray:
+        rgba = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        _check(lib().rt_accum_frame(self._h, rgba.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return rgba
+
+    def read(self) -> np.ndarray:
+        sums = np.empty((self.height, self.width, 3), dtype=np.uint64)
+        _check(lib().rt_accum_read(self._h, sums.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return sums
+
+    def write(self, sums: np.ndarray, samples_done: int) -> None:
+        sums = np.ascontiguousarray(sums, dtype=np.uint64)
+        if sums.shape != (self.height, self.width, 3):
+            raise ValueError("sums must be (H, W, 3) uint64")
+        _check(lib().rt_accum_write(self._h, sums.ctypes.data_as(C.POINTER(C.c_uint64)), samples_done))
+
+    def reset(self) -> None:
+        _check(lib().rt_accum_reset(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            lib().rt_accum_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def render_multi(scenes: list, cam: Camera, params: RtParams, out: np.ndarray | None = None):
+    """rt_render_multi: one frame over several device scenes (same spheres, one Scene per device) of this process."""
+    W, H = params.width, params.height
+    rgba = np.empty((H, W, 4), dtype=np.uint8) if out is None else out
+    arr = (C.c_void_p * len(scenes))(*[s.handle for s in scenes])
+    st = RtStats()
+    cs = cam.c_struct()
+    _check(lib().rt_render_multi(arr, len(scenes), C.byref(cs), C.byref(params), rgba.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                 C.byref(st)))
+    return rgba, st.as_dict()
+
+
+def accum_to_frame(params: RtParams, d_accum: int, total_samples: int, d_rgba: int, device: int, stream: int = 0) -> None:
+    _check(lib().rt_accum_to_frame(C.byref(params), C.c_void_p(d_accum), total_samples, C.c_void_p(d_rgba), device,
+                                   C.c_void_p(stream) if stream else None))
 
 
 def render_pass_device(scene: Scene, cam: Camera, params: RtParams, sample_begin: int, d_accum: int, d_rgba: int = 0,

@@ -72,7 +72,7 @@ def build_oracle() -> None:
     odir = os.path.join(REPO, "oracle")
     subprocess.run(["make", "-s", "-C", odir, "oracle"], check=True)
     if os.path.isdir("/root/reference/programs"):
-        subprocess.run(["make", "-s", "-C", odir, "ref"], check=True)
+        subprocess.run(["make", "-s", "-C", odir, "ref", "ref_O0"], check=True)
 
 
 def build_all(force: bool = False, verbose: bool = False) -> None:

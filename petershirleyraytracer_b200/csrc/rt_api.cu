@@ -78,6 +78,14 @@ struct rt_scene {
     uint64_t last_launches = 0;
 };
 
+struct rt_accum {
+    int device = 0;
+    int W = 0, H = 0;
+    int samples = 0;                          // samples per pixel accumulated so far
+    unsigned long long* d_sums = nullptr;     // W*H*3, 20.44 fixed point, frame pixel order
+    uchar4* d_frame = nullptr;                // write_color over all samples so far (rewritten by every pass)
+};
+
 namespace {
 
 // The cull array of the scene being rendered lives in the (per-device) constant bank.  Renders issued on
@@ -176,7 +184,7 @@ int grow(void** p, size_t* cap, size_t need) {
 }
 
 int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* d_rgba, void* d_sum,
-                  cudaStream_t stream, int sample_base = 0, void* d_frame_accum = nullptr) {
+                  cudaStream_t stream, int sample_base = 0, void* d_frame_accum = nullptr, bool frame_order_out = false) {
     int mode = 0;
     int rc = resolve_scan_mode(sc, p->scan_mode, &mode);
     if (rc) return rc;
@@ -199,7 +207,7 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     a.tiles_x = L.tiles_x; a.tiles_total = L.tiles_total;
     a.shard_rank = p->shard_rank; a.shard_count = p->shard_count;
     a.tiles_local = (L.tiles_total - p->shard_rank + p->shard_count - 1) / p->shard_count;
-    a.compact_out = p->shard_count > 1;
+    a.compact_out = p->shard_count > 1 && !frame_order_out;   // (rt_render_multi: shards store straight into one frame)
     a.out = (uchar4*)d_rgba; a.sum_out = (double*)d_sum;
     a.unit_counter = sc->d_tile_counter; a.stats = sc->d_stats;
     a.sample_base = sample_base; a.frame_accum = (unsigned long long*)d_frame_accum;
@@ -534,6 +542,196 @@ int rt_render_pass(const rt_scene* scene, const rt_camera* cam, const rt_params*
     if (rc) return rc;
     RT_CUDA(cudaMemcpy(accum, d_acc.p, npix * 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     if (rgba_out) RT_CUDA(cudaMemcpy(rgba_out, sc->d_frame, npix * 4, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+// ---- device-resident progressive accumulator (no allocation, no host copy per pass)
+int rt_accum_create(int32_t width, int32_t height, int32_t device, rt_accum** out) {
+    if (!out) return fail(RT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (width < 2 || height < 2 || (int64_t)width * height > (int64_t)1 << 30) return fail(RT_ERR_INVALID, "bad frame size");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed (no CUDA device?)");
+    rt_accum* a = new (std::nothrow) rt_accum();
+    if (!a) return fail(RT_ERR_NOMEM, "host allocation failed");
+    a->device = device; a->W = width; a->H = height;
+    const size_t npix = (size_t)width * height;
+    if (cudaMalloc(&a->d_sums, npix * 3 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&a->d_frame, npix * sizeof(uchar4)) != cudaSuccess ||
+        cudaMemset(a->d_sums, 0, npix * 3 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(a->d_frame, 0, npix * sizeof(uchar4)) != cudaSuccess) {
+        const std::string msg = std::string("rt_accum_create: ") + cudaGetErrorString(cudaGetLastError());
+        cudaFree(a->d_sums); cudaFree(a->d_frame);
+        delete a;
+        return fail(RT_ERR_CUDA, msg);
+    }
+    *out = a;
+    return RT_OK;
+}
+
+void rt_accum_destroy(rt_accum* a) {
+    if (!a) return;
+    DeviceGuard guard(a->device);
+    cudaDeviceSynchronize();
+    cudaFree(a->d_sums); cudaFree(a->d_frame);
+    delete a;
+}
+
+int rt_accum_samples(const rt_accum* a) { return a ? a->samples : RT_ERR_INVALID; }
+
+int rt_accum_reset(rt_accum* a) {
+    if (!a) return fail(RT_ERR_INVALID, "NULL accumulator");
+    DeviceGuard guard(a->device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    RT_CUDA(cudaMemsetAsync(a->d_sums, 0, (size_t)a->W * a->H * 3 * sizeof(unsigned long long), nullptr));
+    a->samples = 0;
+    return RT_OK;
+}
+
+int rt_accum_add(const rt_scene* scene, const rt_camera* cam, const rt_params* p, rt_accum* acc, rt_stats* st) {
+    if (!scene || !cam || !acc) return fail(RT_ERR_INVALID, "NULL argument");
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (p->shard_count != 1) return fail(RT_ERR_INVALID, "rt_accum_add renders whole frames; use rt_render_pass_device for shards");
+    if (p->width != acc->W || p->height != acc->H) return fail(RT_ERR_INVALID, "frame size differs from the accumulator's");
+    rt_scene* sc = const_cast<rt_scene*>(scene);
+    if (sc->device != acc->device) return fail(RT_ERR_INVALID, "scene and accumulator live on different devices");
+    if ((int64_t)acc->samples + p->spp > (1 << 20))
+        return fail(RT_ERR_INVALID, "at most 2^20 samples per pixel in one accumulator (radiance sums are 20.44 fixed point)");
+    DeviceGuard guard(sc->device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->ev1));
+    rc = launch_render(sc, cam, p, acc->d_frame, nullptr, nullptr, acc->samples, acc->d_sums);
+    if (rc) return rc;
+    acc->samples += p->spp;
+    return st ? finish_render(sc, st) : RT_OK;   // without stats the pass stays asynchronous
+}
+
+int rt_accum_frame(const rt_accum* a, uint8_t* rgba_out) {
+    if (!a || !rgba_out) return fail(RT_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(a->device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    RT_CUDA(cudaMemcpy(rgba_out, a->d_frame, (size_t)a->W * a->H * 4, cudaMemcpyDeviceToHost));   // (ordered behind the passes)
+    return RT_OK;
+}
+
+int rt_accum_read(const rt_accum* a, uint64_t* sums_out) {
+    if (!a || !sums_out) return fail(RT_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(a->device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    RT_CUDA(cudaMemcpy(sums_out, a->d_sums, (size_t)a->W * a->H * 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_accum_write(rt_accum* a, const uint64_t* sums, int32_t samples_done) {
+    if (!a || !sums || samples_done < 0 || samples_done > (1 << 20)) return fail(RT_ERR_INVALID, "bad argument");
+    DeviceGuard guard(a->device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    RT_CUDA(cudaMemcpy(a->d_sums, sums, (size_t)a->W * a->H * 3 * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    a->samples = samples_done;
+    return RT_OK;
+}
+
+int rt_accum_to_frame(const rt_params* p, const void* d_accum, int32_t total_samples, void* d_rgba, int32_t device, void* stream) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (!d_accum || !d_rgba || total_samples < 1) return fail(RT_ERR_INVALID, "bad argument");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    const size_t npix = (size_t)p->width * p->height;
+    int grid = (int)((npix + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    rt::accum_to_frame_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned long long*)d_accum, (uchar4*)d_rgba, npix, total_samples);
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
+// ---- the pixel loop on several GPUs of this process
+int rt_render_multi(rt_scene* const* scenes, int32_t n_scenes, const rt_camera* cam, const rt_params* p, uint8_t* rgba_out,
+                    rt_stats* st) {
+    if (!scenes || n_scenes < 1 || !cam || !rgba_out) return fail(RT_ERR_INVALID, "NULL argument");
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (p->shard_count != 1) return fail(RT_ERR_INVALID, "rt_render_multi deals the shards itself: shard_count must be 1");
+    for (int i = 0; i < n_scenes; ++i) {
+        if (!scenes[i]) return fail(RT_ERR_INVALID, "NULL scene");
+        if (scenes[i]->n != scenes[0]->n) return fail(RT_ERR_INVALID, "the scenes of a group hold the same spheres (one copy per device)");
+        for (int j = 0; j < i; ++j) if (scenes[j] == scenes[i]) return fail(RT_ERR_INVALID, "a scene handle appears twice");
+    }
+    rt_scene* sc0 = scenes[0];
+    const size_t npix = (size_t)p->width * p->height;
+    // peer access from every device to the first one: its frame receives all stores
+    bool peer_ok = true;
+    for (int i = 1; i < n_scenes && peer_ok; ++i) {
+        if (scenes[i]->device == sc0->device) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, scenes[i]->device, sc0->device) != cudaSuccess || !can) { cudaGetLastError(); peer_ok = false; break; }
+        DeviceGuard g(scenes[i]->device);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(sc0->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) peer_ok = false;
+        cudaGetLastError();
+    }
+    {
+        DeviceGuard g0(sc0->device);
+        if (!g0.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+        rc = grow(&sc0->d_frame, &sc0->frame_cap, npix * 4);
+        if (rc) return rc;
+    }
+    rt_tile_layout L;
+    rt_params q = *p;
+    q.shard_count = n_scenes;
+    tile_layout(&q, &L);
+    // launch every shard (asynchronous, one stream per device), then wait for all of them
+    for (int i = 0; i < n_scenes; ++i) {
+        rt_scene* sc = scenes[i];
+        DeviceGuard g(sc->device);
+        if (!g.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+        if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->ev1));
+        q.shard_rank = i;
+        if (peer_ok) {
+            rc = launch_render(sc, cam, &q, sc0->d_frame, nullptr, nullptr, 0, nullptr, /*frame_order_out=*/true);
+        } else {
+            if (i > 0) { rc = grow(&sc->d_frame, &sc->frame_cap, (size_t)L.shard_bytes); if (rc) return rc; }
+            rc = launch_render(sc, cam, &q, i == 0 ? (void*)((char*)sc0->d_frame) : sc->d_frame, nullptr, nullptr, 0, nullptr,
+                               /*frame_order_out=*/i == 0);
+        }
+        if (rc) return rc;
+    }
+    rt_stats total;
+    std::memset(&total, 0, sizeof total);
+    for (int i = 0; i < n_scenes; ++i) {
+        DeviceGuard g(scenes[i]->device);
+        rt_stats one;
+        rc = finish_render(scenes[i], &one);
+        if (rc) return rc;
+        total.kernel_ms = one.kernel_ms > total.kernel_ms ? one.kernel_ms : total.kernel_ms;   // the shards run concurrently
+        total.samples += one.samples; total.casts += one.casts; total.sphere_tests += one.sphere_tests;
+        total.node_tests += one.node_tests; total.exact_tests += one.exact_tests; total.black += one.black;
+        total.early_outs += one.early_outs; total.primary_hits += one.primary_hits; total.overflows += one.overflows;
+        total.launches += one.launches; total.self_resolved += one.self_resolved;
+    }
+    {
+        DeviceGuard g0(sc0->device);
+        RT_CUDA(cudaMemcpy(rgba_out, sc0->d_frame, npix * 4, cudaMemcpyDeviceToHost));
+    }
+    if (!peer_ok) {
+        // no peer access between these devices: the other shards come back as compact tile buffers and are placed on the host
+        std::vector<uint8_t> shard((size_t)L.shard_bytes);
+        for (int i = 1; i < n_scenes; ++i) {
+            DeviceGuard g(scenes[i]->device);
+            RT_CUDA(cudaMemcpy(shard.data(), scenes[i]->d_frame, (size_t)L.shard_bytes, cudaMemcpyDeviceToHost));
+            for (int l = 0; l < L.tiles_per_shard; ++l) {
+                const int t = l * n_scenes + i;
+                if (t >= L.tiles_total) break;
+                const int ty = t / L.tiles_x, tx = t - ty * L.tiles_x;
+                for (int py = 0; py < rt::kTileH && ty * rt::kTileH + py < p->height; ++py)
+                    for (int px = 0; px < rt::kTileW && tx * rt::kTileW + px < p->width; ++px)
+                        std::memcpy(rgba_out + 4 * ((size_t)(ty * rt::kTileH + py) * p->width + tx * rt::kTileW + px),
+                                    shard.data() + 4 * ((size_t)l * rt::kTilePix + py * rt::kTileW + px), 4);
+            }
+        }
+    }
+    if (st) *st = total;
     return RT_OK;
 }
 

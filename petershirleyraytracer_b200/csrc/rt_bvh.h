@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 
 namespace rt {
@@ -355,6 +356,7 @@ inline void build_bvh(const double* centres, const double* radii, int n, BvhHost
 // reach the device accepts (rho_max), the FP32 rounding of o and of the cell arithmetic.  Cells that would need
 // more than four entries carry kTieOverfull and send the cast to the BVH traversal instead (always correct).
 constexpr int kTieGiants = 4;
+constexpr double kTieCellRadii = 2.0;   // cell size in median sphere radii (doubled until giants / cell budget fit)
 constexpr int32_t kTieOverfull = -2;
 constexpr double kTieShell = 1.9073486328125e-06;   // 2^-19 = 32 * 2^-24: FP32 error of the shell quantity is <= 2^-24 (14 (o^2 + c^2) + 4 r^2)
 
@@ -386,7 +388,8 @@ inline void build_tie_grid(const double* c, const double* r, int n, TieGridHost*
     const double r_med = sorted[(size_t)n / 2];
     if (!(r_med >= 1e-12) || !(cmax <= 1e12)) return;   // FP32 shell arithmetic needs moderate magnitudes
 
-    double h = 2.0 * r_med;
+    double h = kTieCellRadii * r_med;
+    if (const char* e = std::getenv("RT_TIE_CELL")) { const double v = std::atof(e); if (v > 0.1 && v < 100.0) h = v * r_med; }   // tuning experiments only
     for (int attempt = 0; attempt < 24; ++attempt, h *= 2.0) {
         const double rho_max = h / 64.0;
         // pass 1: giants (by the number of cells their box would cover) and the bounds of everything else

@@ -409,8 +409,9 @@ __device__ __forceinline__ bool exact_test_unordered(const double4* __restrict__
 #define RT_BVH_LEAF 1   // spheres per leaf (== rt_bvh.h: kBvhLeafMax)
 #endif
 constexpr int kBvhW = RT_BVH_WIDTH;  // children per device BVH node (== rt_bvh.h: kBvhWidth)
+static_assert(RT_BVH_WIDTH == 4 && RT_BVH_LEAF == 1, "the traversal is written for 4-wide nodes with single-sphere leaves (8-wide nodes and 2-6 sphere leaves were measured slower in round 1)");
 constexpr int kBvhStack = 48;
-// `best` is in/out: a hit already known (the start sphere's, see tie_resolve) bounds the traversal from the first
+// `best` is in/out: a hit already known (the start sphere's, see self_cast) bounds the traversal from the first
 // node on; `skip` names a sphere that needs no further test (that start sphere; -1: none).
 __device__ __forceinline__ void bvh_cast(const SceneDev& sc, double ox, double oy, double oz, double dx, double dy,
                                          double dz, double A, double tmin, double tmax, Best& best, int skip,
@@ -504,30 +505,23 @@ __device__ __forceinline__ void bvh_cast(const SceneDev& sc, double ox, double o
                 if (zz) hit[i] = hit[i] && lz[i] <= opz && hz[i] >= omz;
             }
         }
-        // hit leaves are resolved on the spot (each re-checked against the best found so far)
+        // hit leaves are resolved on the spot, one after the other in ONE rolled loop (each re-checked against the best
+        // found so far): a single copy of the FP64 test in the instruction stream -- with one copy per child slot the
+        // kernel outgrew the 32 KB instruction cache and stalled on instruction fetch
+        uint32_t leafm = 0u;
 #pragma unroll
-        for (int i = 0; i < W; ++i) {
-            if (hit[i] && ch[i] < 0 && tn[i] <= bu) {
-                const int first = (int)(((unsigned)ch[i] & 0x7fffffffu) >> 3), count = ch[i] & 7;
-#if RT_BVH_LEAF == 1
-                {   // single-sphere leaves: no loop over the leaf (its branch overhead was ~4 % of the traversal)
-                    (void)count;
-                    const int k = first;   // (single-sphere leaves carry the sphere index itself, rt_bvh.h)
-                    if (k != skip) {
-                        ++n_exact;
-                        if (exact_test_unordered(sc.exact, k, ox, oy, oz, dx, dy, dz, dA, tmin, tmax, best))
-                            bu = __fmul_ru(__double2float_ru(best.t), kInvDn);
-                    }
-                }
-#else
-                for (int j = 0; j < count; ++j) {
-                    const int k = __ldg(sc.bvh_leaf + first + j);
-                    if (k == skip) continue;
-                    ++n_exact;
-                    if (exact_test_unordered(sc.exact, k, ox, oy, oz, dx, dy, dz, dA, tmin, tmax, best))
-                        bu = __fmul_ru(__double2float_ru(best.t), kInvDn);
-                }
-#endif
+        for (int i = 0; i < W; ++i) leafm |= (hit[i] && ch[i] < 0) ? (1u << i) : 0u;
+#pragma unroll 1
+        while (leafm) {
+            const int i = __ffs((int)leafm) - 1;
+            leafm &= leafm - 1u;
+            const float tni = i == 0 ? tn[0] : (i == 1 ? tn[1] : (i == 2 ? tn[2] : tn[3]));
+            const int chi = i == 0 ? ch[0] : (i == 1 ? ch[1] : (i == 2 ? ch[2] : ch[3]));
+            const int k = (int)(((unsigned)chi & 0x7fffffffu) >> 3);   // single-sphere leaves carry the sphere index itself (rt_bvh.h)
+            if (tni <= bu && k != skip) {
+                ++n_exact;
+                if (exact_test_unordered(sc.exact, k, ox, oy, oz, dx, dy, dz, dA, tmin, tmax, best))
+                    bu = __fmul_ru(__double2float_ru(best.t), kInvDn);
             }
         }
         // hit inner children: descend into the nearest, stack the others
@@ -581,55 +575,57 @@ __device__ __forceinline__ bool tie_candidate(const float4 s, float fx, float fy
     return !(fabsf(q) > tol);   // (NaN counts as a candidate)
 }
 
-__device__ __forceinline__ bool tie_resolve(const SceneDev& sc, int self, double ox, double oy, double oz, double dx,
-                                            double dy, double dz, const RcpA& dA, double tmin, Best& best,
-                                            uint32_t& n_exact) {
-    const double kInf = __longlong_as_double(0x7ff0000000000000ll);
-    float rho = 0.f;
-    if (best.t != 0.0) {   // reach = t * |dir|, rounded up
-        rho = __fmul_ru(__fmul_ru(__double2float_ru(best.t), __fsqrt_ru(__double2float_ru(dA.A))), 1.0000019f);
-        if (!(rho <= sc.tie_rho_max)) return false;   // (also NaN / negative t)
-    }
-    const float fx = (float)ox, fy = (float)oy, fz = (float)oz;
-    const float o2 = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
-#pragma unroll 1
-    for (int g = 0; g < sc.tie_ngiants; ++g) {
-        const int j = sc.tie_giants[g];
-        if (j != self && tie_candidate(__ldg(sc.sph32 + j), fx, fy, fz, o2, rho)) {
-            ++n_exact;
-            exact_test_unordered(sc.exact, j, ox, oy, oz, dx, dy, dz, dA, tmin, kInf, best);
-        }
-    }
-    const bool inside = fx >= sc.tie_g0[0] && fx <= sc.tie_g1[0] && fy >= sc.tie_g0[1] && fy <= sc.tie_g1[1] &&
-                        fz >= sc.tie_g0[2] && fz <= sc.tie_g1[2];
-    if (inside) {   // outside the grid no listed sphere has its (padded) box around o
-        const int ix = (int)((fx - sc.tie_g0[0]) * sc.tie_inv_h), iy = (int)((fy - sc.tie_g0[1]) * sc.tie_inv_h),
-                  iz = (int)((fz - sc.tie_g0[2]) * sc.tie_inv_h);
-        const int4 cell = __ldg(sc.tie_cells + ((size_t)iz * sc.tie_dimy + iy) * sc.tie_dimx + ix);
-        if (cell.x == -2) return false;
-        const int js[4] = {cell.x, cell.y, cell.z, cell.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int j = js[e];
-            if (j >= 0 && j != self && tie_candidate(__ldg(sc.sph32 + j), fx, fy, fz, o2, rho)) {
-                ++n_exact;
-                exact_test_unordered(sc.exact, j, ox, oy, oz, dx, dy, dz, dA, tmin, kInf, best);
-            }
-        }
-    }
-    return true;
-}
-
 // The part of a BVH-mode cast that needs no traversal: FP64 sphere::hit of the start sphere, then the tie grid.
-// Returns true if `best` is the cast's final answer.
+// Returns true if `best` is the cast's final answer; false if the cast cannot be decided here (not a hit of the
+// start sphere, reach too long, overfull cell): the caller traverses with `best` as the initial bound.  (tmax = +inf.)
+// One rolled loop over the candidates -- entry 0 is the start sphere, then the giants, then the cell's spheres -- so
+// that the FP64 test exists once in the instruction stream.
 __device__ __forceinline__ bool self_cast(const SceneDev& sc, int self, double ox, double oy, double oz, double dx,
                                           double dy, double dz, double A, double tmin, Best& best, uint32_t& n_exact) {
     if (self < 0) return false;
     const RcpA dA = make_rcp(A);
-    ++n_exact;
-    exact_test_unordered(sc.exact, self, ox, oy, oz, dx, dy, dz, dA, tmin, __longlong_as_double(0x7ff0000000000000ll), best);
-    if (!(sc.tie_ok && best.k == self && dA.fast)) return false;
-    return tie_resolve(sc, self, ox, oy, oz, dx, dy, dz, dA, tmin, best, n_exact);
+    const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+    bool decided = false;
+    int ncand = 1;
+    int4 cell = make_int4(-1, -1, -1, -1);
+    float fx = 0.f, fy = 0.f, fz = 0.f, o2 = 0.f, rho = 0.f;
+#pragma unroll 1
+    for (int e = 0; e < ncand; ++e) {
+        int j = self;
+        bool test = true;
+        if (e > 0) {
+            const int g = e - 1 - sc.tie_ngiants;
+            if (g < 0) j = sc.tie_giants[e - 1];
+            else j = g == 0 ? cell.x : (g == 1 ? cell.y : (g == 2 ? cell.z : cell.w));
+            test = j != self && tie_candidate(__ldg(sc.sph32 + j), fx, fy, fz, o2, rho);
+        }
+        if (test) {
+            ++n_exact;
+            exact_test_unordered(sc.exact, j, ox, oy, oz, dx, dy, dz, dA, tmin, kInf, best);
+        }
+        if (e == 0) {
+            if (!(sc.tie_ok && best.k == self && dA.fast)) break;
+            if (best.t != 0.0) {   // reach = t * |dir|, rounded up
+                rho = __fmul_ru(__fmul_ru(__double2float_ru(best.t), __fsqrt_ru(__double2float_ru(A))), 1.0000019f);
+                if (!(rho <= sc.tie_rho_max)) break;   // (also NaN / negative t)
+            }
+            fx = (float)ox; fy = (float)oy; fz = (float)oz;
+            o2 = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
+            int ncell = 0;
+            const bool inside = fx >= sc.tie_g0[0] && fx <= sc.tie_g1[0] && fy >= sc.tie_g0[1] && fy <= sc.tie_g1[1] &&
+                                fz >= sc.tie_g0[2] && fz <= sc.tie_g1[2];
+            if (inside) {   // outside the grid no listed sphere has its (padded) box around o
+                const int ix = (int)((fx - sc.tie_g0[0]) * sc.tie_inv_h), iy = (int)((fy - sc.tie_g0[1]) * sc.tie_inv_h),
+                          iz = (int)((fz - sc.tie_g0[2]) * sc.tie_inv_h);
+                cell = __ldg(sc.tie_cells + ((size_t)iz * sc.tie_dimy + iy) * sc.tie_dimx + ix);
+                if (cell.x == -2) break;   // overfull cell
+                ncell = (cell.x >= 0) + (cell.y >= 0) + (cell.z >= 0) + (cell.w >= 0);   // (entries fill from .x up)
+            }
+            ncand = 1 + sc.tie_ngiants + ncell;
+            decided = true;
+        }
+    }
+    return decided;
 }
 
 // hittable_list::hit for one ray given its survivors (or the full list when ovf): list order, shrinking tmax.

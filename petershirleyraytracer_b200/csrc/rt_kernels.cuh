@@ -386,7 +386,39 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R>::kMinBlocks) render_
 //   regeneration: freed records take the warp's next (pixel, sample) ids and enter T as primary rays.
 // The queues compact: each phase runs with (nearly) all 32 lanes whatever mix of trapped, escaping and new paths
 // the pool holds.  Radiance sums, units, chunk bookkeeping and write_color are the linear-scan kernel's.
-constexpr int kPool = 64;   // path records per warp
+#ifndef RT_WAVE_POOL
+#define RT_WAVE_POOL 96
+#endif
+#ifndef RT_WAVE_REGEN
+#define RT_WAVE_REGEN 24
+#endif
+constexpr int kPool = RT_WAVE_POOL;        // path records per warp
+constexpr int kRegenMin = RT_WAVE_REGEN;   // free records are refilled in batches of at least this many (a regeneration
+                                           // round costs the same for 2 lanes as for 32), so (kPool - kRegenMin) / 2 >= 32
+                                           // keeps both phases at full width
+
+// acc += v for a 64-bit fixed-point sum in shared memory, as two native 32-bit atomics with an explicit carry
+// (a 64-bit shared-memory atomicAdd compiles to a compare-and-swap loop, ~65 instructions per call site).  All
+// additions of a round are complete before anybody reads the sum (the __syncwarp() at the top of the main loop).
+__device__ __forceinline__ void fixed_add(unsigned long long* acc, unsigned long long v) {
+    unsigned int* w = reinterpret_cast<unsigned int*>(acc);   // little endian: w[0] = low word
+    const unsigned int lo = (unsigned int)v, hi = (unsigned int)(v >> 32);
+    const unsigned int old = atomicAdd(w, lo);
+    const unsigned int carry = (old + lo < old) ? 1u : 0u;
+    if (hi | carry) atomicAdd(w + 1, hi + carry);
+}
+
+// Cold paths of the wavefront kernel, out of line: its two phases are long straight-line code that every warp streams
+// through once per round, so the kernel's hot instruction footprint has to stay inside the 32 KB instruction cache
+// (the first version, everything inlined, was 82 KB and spent 3 stall cycles per issued instruction on fetch).
+__device__ __noinline__ void flush_unit_cold(const RenderArgs& a, Unit u, unsigned long long* accp, int lane) {
+    flush_unit(a, u, accp, lane);
+}
+__device__ __noinline__ void full_scan_cold(const SceneDev& sc, double ox, double oy, double oz, double dx, double dy,
+                                            double dz, double A, double tmin, Best* best, uint32_t* n_exact) {
+    *best = resolve_hits(sc, true, 0, nullptr, 0, ox, oy, oz, dx, dy, dz, A, tmin, __longlong_as_double(0x7ff0000000000000ll),
+                         *n_exact);
+}
 
 struct WaveSmem { uint32_t acc_off, state_off, meta_off, bt_off, bk_off, self_off, q_off, total; };
 __host__ __device__ inline WaveSmem wave_smem() {
@@ -403,7 +435,7 @@ __host__ __device__ inline WaveSmem wave_smem() {
 }
 
 #ifndef RT_WAVE_MINB
-#define RT_WAVE_MINB 5
+#define RT_WAVE_MINB 4   // 128 registers: at 5 CTAs/SM (96) the two phases spill ~230 bytes and run 12 % slower
 #endif
 __global__ void __launch_bounds__(kThreads, RT_WAVE_MINB) render_wave_kernel(const __grid_constant__ RenderArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -426,23 +458,26 @@ __global__ void __launch_bounds__(kThreads, RT_WAVE_MINB) render_wave_kernel(con
     int nS = 0, nT = 0, nF = kPool;   // queue lengths (warp-uniform)
     int infl0 = 0, infl1 = 0;         // records in flight per unit buffer (warp-uniform)
 
-    const double wm1 = (double)(a.W - 1), hm1 = (double)(a.H - 1);
+    const RcpA rcp_w = make_rcp((double)(a.W - 1)), rcp_h = make_rcp((double)(a.H - 1));   // divisors of programs/main.cc:80-81
     const double kInf = __longlong_as_double(0x7ff0000000000000ll);
     uint32_t n_samples = 0, n_casts = 0, n_exact = 0, n_black = 0, n_early = 0, n_primary = 0, n_ovf = 0, n_nodes = 0, n_self = 0;
 
     Unit u0, u1;
     u0.valid = u1.valid = 0; u0.total = u0.next = u1.total = u1.next = 0; u0.tile_l = u1.tile_l = u0.chunk = u1.chunk = 0;
+    TileGeom geo;                 // of the unit that is handing out samples (cur)
+    geo.x0 = geo.y0 = 0; geo.tw = geo.th = 1;
+    uint32_t unit_ns = 1, unit_s0 = 0;   // its samples per pixel and first sample index
     int cur = 0;
     bool no_more = false;
 
     for (;;) {
         __syncwarp();   // queue / record writes of the last phase are visible to every lane
         // ---------------- retire units whose samples are all traced
-        if (u0.valid && u0.next >= u0.total && infl0 == 0) { flush_unit(a, u0, acc, lane); u0.valid = 0; }
-        if (u1.valid && u1.next >= u1.total && infl1 == 0) { flush_unit(a, u1, acc + kTilePix * 3, lane); u1.valid = 0; }
+        if (u0.valid && u0.next >= u0.total && infl0 == 0) { flush_unit_cold(a, u0, acc, lane); u0.valid = 0; }
+        if (u1.valid && u1.next >= u1.total && infl1 == 0) { flush_unit_cold(a, u1, acc + kTilePix * 3, lane); u1.valid = 0; }
 
         // ---------------- regeneration: free records take the next (pixel, sample) ids
-        while (nF > 0) {
+        while (nF >= kRegenMin || (nF > 0 && nS == 0 && nT == 0)) {
             Unit c = cur ? u1 : u0;
             if (!c.valid || c.next >= c.total) {
                 const int np = c.valid ? (cur ^ 1) : cur;
@@ -455,19 +490,21 @@ __global__ void __launch_bounds__(kThreads, RT_WAVE_MINB) render_wave_kernel(con
                 c.valid = 1;
                 c.tile_l = (int)(id / (unsigned)a.chunks);
                 c.chunk = (int)(id - (unsigned)c.tile_l * (unsigned)a.chunks);
-                const TileGeom g = tile_geom(a, c.tile_l);
-                c.total = (uint32_t)(g.tw * g.th) * (uint32_t)unit_spp(a, c.chunk);
+                geo = tile_geom(a, c.tile_l);
+                unit_ns = (uint32_t)unit_spp(a, c.chunk);
+                unit_s0 = (uint32_t)(a.sample_base + c.chunk * a.chunk_spp);
+                c.total = (uint32_t)(geo.tw * geo.th) * unit_ns;
                 c.next = 0;
                 cur = np;
             }
             const uint32_t avail = c.total - c.next;
             const int m = (int)min((uint32_t)min(nF, 32), avail);
             if (lane < m) {
-                const TileGeom g = tile_geom(a, c.tile_l);
+                const TileGeom g = geo;
                 const uint32_t id = c.next + (uint32_t)lane;
-                const uint32_t ns = (uint32_t)unit_spp(a, c.chunk);
+                const uint32_t ns = unit_ns;
                 const uint32_t p = id / ns;
-                const uint32_t s = (uint32_t)(a.sample_base + c.chunk * a.chunk_spp) + (id - p * ns);
+                const uint32_t s = unit_s0 + (id - p * ns);
                 const int ly = (int)p / g.tw, lx = (int)p - ly * g.tw;
                 const int i = g.x0 + lx, j = a.H - 1 - (g.y0 + ly);  // j from the bottom (programs/main.cc:72)
                 const uint32_t pixid = (uint32_t)(j * a.W + i);
@@ -476,8 +513,8 @@ __global__ void __launch_bounds__(kThreads, RT_WAVE_MINB) render_wave_kernel(con
                     const uint4 w = philox4x32_10(pixid, s, 0u, 0u, a.key0, a.key1);
                     xu = u32_unit(w.x); xv = u32_unit(w.y);
                 }
-                const double u = ddiv(dadd((double)i, xu), wm1);  // programs/main.cc:80
-                const double v = ddiv(dadd((double)j, xv), hm1);  // programs/main.cc:81
+                const double u = ddiv_t(dadd((double)i, xu), rcp_w);  // programs/main.cc:80 (== IEEE quotient, ddiv_t)
+                const double v = ddiv_t(dadd((double)j, xv), rcp_h);  // programs/main.cc:81
                 double dx, dy, dz;
                 camera_ray(a.cam_org, a.cam_llc, a.cam_hor, a.cam_ver, u, v, dx, dy, dz);
                 ++n_samples;
@@ -529,9 +566,9 @@ __global__ void __launch_bounds__(kThreads, RT_WAVE_MINB) render_wave_kernel(con
                     sky_color(a.sh, dy, A, bounces, cr, cg, cb);
                     const double fs = (double)(1ull << kFixShift);
                     unsigned long long* ap = acc + (buf * kTilePix + (lp & 63)) * 3;
-                    atomicAdd(ap + 0, __double2ull_rz(cr * fs));
-                    atomicAdd(ap + 1, __double2ull_rz(cg * fs));
-                    atomicAdd(ap + 2, __double2ull_rz(cb * fs));
+                    fixed_add(ap + 0, __double2ull_rz(cr * fs));
+                    fixed_add(ap + 1, __double2ull_rz(cg * fs));
+                    fixed_add(ap + 2, __double2ull_rz(cb * fs));
                     dest = 3;
                 } else {
                     Best hitb;
@@ -603,7 +640,7 @@ __global__ void __launch_bounds__(kThreads, RT_WAVE_MINB) render_wave_kernel(con
                 }
                 if (seq) {
                     ++n_ovf;
-                    best = resolve_hits(a.sc, true, 0, nullptr, 0, ox, oy, oz, dx, dy, dz, A, a.tmin, kInf, n_exact);
+                    full_scan_cold(a.sc, ox, oy, oz, dx, dy, dz, A, a.tmin, &best, &n_exact);
                 }
                 bt[rec] = best.t;
                 bk[rec] = best.k < 0 ? -1 : (best.k | (best.C == 0.0 ? (1 << 30) : 0));
@@ -619,9 +656,9 @@ __global__ void __launch_bounds__(kThreads, RT_WAVE_MINB) render_wave_kernel(con
                           ST_SELF_RESOLVED};
 #pragma unroll
     for (int c = 0; c < 9; ++c) {
-        unsigned long long v = vals[c];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        // (two 16-bit halves: a lane's counter can approach 2^32, the warp sum of a half stays below 2^21)
+        const unsigned lo = __reduce_add_sync(0xffffffffu, vals[c] & 0xffffu), hi = __reduce_add_sync(0xffffffffu, vals[c] >> 16);
+        const unsigned long long v = (unsigned long long)lo + ((unsigned long long)hi << 16);
         if (lane == 0 && v) atomicAdd(&a.stats[slots[c]], v);
     }
 }
@@ -813,6 +850,23 @@ __global__ void deinterleave_kernel(const uchar4* __restrict__ gathered, uchar4*
         frame[idx] = gathered[((size_t)rank * tiles_per_shard + l) * kTilePix + p];
     }
     (void)tiles_total;
+}
+
+// write_color (programs/color.h:16-23) over a frame-ordered fixed-point accumulator: the last step of a render whose
+// SAMPLES were split over ranks (integer all-reduce of the sums first; order-independent, so the frame is the
+// single-GPU frame bit for bit).
+__global__ void accum_to_frame_kernel(const unsigned long long* __restrict__ accum, uchar4* __restrict__ frame, size_t npix,
+                                      int total_samples) {
+    const double one_over_samples = ddiv(1.0, (double)total_samples);
+    const double inv_fs = 1.0 / (double)(1ull << kFixShift);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        uchar4 q;
+        q.x = (unsigned char)write_color_channel(__ull2double_rn(accum[3 * i]) * inv_fs, one_over_samples);
+        q.y = (unsigned char)write_color_channel(__ull2double_rn(accum[3 * i + 1]) * inv_fs, one_over_samples);
+        q.z = (unsigned char)write_color_channel(__ull2double_rn(accum[3 * i + 2]) * inv_fs, one_over_samples);
+        q.w = 255;
+        frame[i] = q;
+    }
 }
 
 // Small device-side mirrors for the per-function parity tests.

@@ -82,9 +82,12 @@ def oracle() -> C.CDLL:
     return _cache["orc"]
 
 
-def ref() -> C.CDLL:
-    if "ref" not in _cache:
-        L = C.CDLL(REF_SO)
+def ref(opt: str = "") -> C.CDLL:
+    """oracle/_ref/libref.so; opt="O0": the same sources built without optimisation (the reference's own CMake
+    configuration, programs/CMakeLists.txt:1-6), used only for bench.py's cpu_baseline of config 1."""
+    key = "ref" + opt
+    if key not in _cache:
+        L = C.CDLL(REF_SO if not opt else REF_SO.replace("libref.so", f"libref_{opt}.so"))
         L.ref_main_ppm.restype = C.c_long
         L.ref_main_ppm.argtypes = [C.c_uint64, C.c_char_p, C.c_long]
         L.ref_render_rows.argtypes = [dp, dp, C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int,
@@ -101,8 +104,12 @@ def ref() -> C.CDLL:
         L.ref_write_color_batch.argtypes = [dp, C.c_int, C.c_int, ip]
         L.ref_random_in_hemisphere_batch.argtypes = [dp, u64p, C.c_int, dp]
         L.ref_max_threads.restype = C.c_int
-        _cache["ref"] = L
-    return _cache["ref"]
+        _cache[key] = L
+    return _cache[key]
+
+
+def have_ref_O0() -> bool:
+    return os.path.exists(REF_SO.replace("libref.so", "libref_O0.so"))
 
 
 def _f64(a):
@@ -136,6 +143,11 @@ def render(which: str, centres, radii, cam12, W, H, spp, max_depth=50, seed=0, r
         return rgb, sums, st.as_dict()
     assert rng_mode == RNG_RAND15 and not early_out and not want_sums
     stats = np.zeros(3, dtype=np.float64)
+    if which == "refO0":
+        assert shading is None
+        ref("O0").ref_render_rows(_p(centres), _p(radii), len(radii), _p(cam12), W, H, spp, max_depth, seed, j0, j1, nthreads,
+                                  rgb.ctypes.data_as(u8p), _p(stats))
+        return rgb, None, {"samples": stats[0], "casts": stats[1], "black": stats[2]}
     if shading is not None:
         ref().ref_render_rows_param(_p(centres), _p(radii), len(radii), _p(cam12), W, H, spp, max_depth, seed,
                                     C.byref(shading), j0, j1, nthreads, rgb.ctypes.data_as(u8p), _p(stats))

@@ -825,3 +825,154 @@ def test_two_host_threads_share_the_constant_bank(rt, book, default_scene):
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errs, errs
+
+
+# ------------------------------------------------------------------ round 2: device-resident accumulator, multi-GPU behind the C ABI
+@pytest.mark.parametrize("mode", [0, 3])
+def test_accumulator_passes_equal_one_render(rt, book, mode):
+    """rt_accum_*: the sums stay on the device between passes; any split of the samples leaves the single-render frame
+    and sums bit for bit; read / write move a checkpoint to another accumulator."""
+    from petershirleyraytracer_b200 import scenes
+    c, r = book
+    W, H, spp = 88, 56, 14
+    cam = scenes.book_camera(W, H)
+    with rt.Scene(c, r) as sc, rt.Accumulator(W, H) as acc, rt.Accumulator(W, H) as acc2:
+        full, sums, st = rt.render(sc, cam, rt.make_params(W, H, spp, 50, seed=5, scan_mode=mode, early_out=False), want_sums=True)
+        casts = 0
+        for n in (5, 1, 2):
+            casts += acc.add(sc, cam, rt.make_params(W, H, n, 50, seed=5, scan_mode=mode, early_out=False), want_stats=True)["casts"]
+        assert acc.samples == 8
+        acc2.write(acc.read(), acc.samples)                      # checkpoint -> resume elsewhere
+        for a in (acc, acc2):
+            a.add(sc, cam, rt.make_params(W, H, 6, 50, seed=5, scan_mode=mode, early_out=False))   # asynchronous pass
+        f1, f2 = acc.frame(), acc2.frame()
+        s1 = acc.read()
+        with pytest.raises(rt.RtError):
+            acc.add(sc, cam, rt.make_params(W + 8, H, 1, 50))
+        acc.reset()
+        assert acc.samples == 0 and not acc.read().any()
+    assert np.array_equal(f1, full) and np.array_equal(f2, full)
+    assert np.array_equal(s1.astype(np.float64) / 2.0**44, sums)
+    assert casts < st["casts"]
+
+
+def test_accumulator_64_passes_cost_one_render(rt, book):
+    """a 64-pass progressive render of the 1200x800 frame through the device-resident accumulator
+    against one render of the same samples (wall clock around both, GPU idle before each)."""
+    import time
+    import torch
+    from petershirleyraytracer_b200 import scenes
+    c, r = book
+    W, H, spp, passes = 1200, 800, 256, 64
+    cam = scenes.book_camera(W, H)
+    with rt.Scene(c, r) as sc, rt.Accumulator(W, H) as acc:
+        p = rt.make_params(W, H, spp, 50, seed=2, early_out=False, scan_mode=0)
+        rt.render_device(sc, cam, rt.make_params(W, H, 4, 50, seed=2, early_out=False, scan_mode=0), torch.empty(W * H * 4, dtype=torch.uint8, device="cuda").data_ptr())
+        rt.render_finish(sc)
+        frame = torch.empty(W * H * 4, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rt.render_device(sc, cam, p, frame.data_ptr())
+        rt.render_finish(sc)
+        t_one = time.perf_counter() - t0
+        pp = rt.make_params(W, H, spp // passes, 50, seed=2, early_out=False, scan_mode=0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(passes):
+            acc.add(sc, cam, pp)
+        rgba = acc.frame()
+        t_prog = time.perf_counter() - t0
+        assert np.array_equal(rgba, frame.cpu().numpy().reshape(H, W, 4))
+    _record_parity("progressive_64_passes_1200x800x256spp", {"single_render_s": t_one, "64_passes_s": t_prog, "ratio": t_prog / t_one})
+    assert t_prog < 1.05 * t_one + 0.01
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_render_multi_equals_single_device(rt, book, n):
+    """rt_render_multi: the shards of several device scenes store straight into one frame.  With the scenes on the same
+    device this runs on a 1-GPU box; test_render_multi_two_devices covers real peers."""
+    from petershirleyraytracer_b200 import scenes
+    c, r = book
+    W, H, spp = 150, 100, 6
+    cam = scenes.book_camera(W, H)
+    p = rt.make_params(W, H, spp, 50, seed=8)
+    group = [rt.Scene(c, r) for _ in range(n)]
+    try:
+        full, _, st = rt.render(group[0], cam, p)
+        multi, mst = rt.render_multi(group, cam, p)
+        lin, lst = rt.render_multi(group, cam, rt.make_params(W, H, spp, 50, seed=8, scan_mode=0))
+    finally:
+        for s in group:
+            s.close()
+    assert np.array_equal(multi, full) and np.array_equal(lin, full)
+    assert mst["casts"] == st["casts"] == lst["casts"] and mst["samples"] == W * H * spp and mst["launches"] == n
+
+
+def test_render_multi_two_devices(rt, book):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from petershirleyraytracer_b200 import scenes
+    c, r = book
+    W, H, spp = 300, 200, 8
+    cam = scenes.book_camera(W, H)
+    p = rt.make_params(W, H, spp, 50, seed=8)
+    ndev = min(torch.cuda.device_count(), 8)
+    group = [rt.Scene(c, r, device=d) for d in range(ndev)]
+    try:
+        full, _, st = rt.render(group[0], cam, p)
+        multi, mst = rt.render_multi(group, cam, p)
+    finally:
+        for s in group:
+            s.close()
+    assert np.array_equal(multi, full) and mst["casts"] == st["casts"]
+
+
+def test_host_main_multi_gpu_frame_equals_single(rt):
+    """rt_main --gpus N (rt::render over a device_world_group -> rt_render_multi) prints the text rt_main prints on one
+    device.  On a 1-GPU box the group is the same device twice (RT_MAIN_DEVICES=0,0)."""
+    import os
+    import subprocess
+    import torch
+    exe = os.path.join(os.path.dirname(rt.LIB_PATH), "rt_main")
+    if not os.path.exists(exe):
+        pytest.skip("rt_main not built")
+    one = subprocess.run([exe, "160", "6", "50", "11"], capture_output=True, check=True)
+    env = dict(os.environ)
+    args = [exe, "160", "6", "50", "11"]
+    if torch.cuda.device_count() >= 2:
+        args += ["--gpus", "2"]
+    else:
+        env["RT_MAIN_DEVICES"] = "0,0"
+    two = subprocess.run(args, capture_output=True, check=True, env=env)
+    assert two.stdout == one.stdout and b"Rendered on 2 device worlds" in two.stderr
+    assert one.stdout.startswith(b"P3\n160 90\n255\n")
+
+
+def test_sample_split_equals_single_render(rt, book):
+    """dist.render_sample_split on one GPU: three 'ranks' trace sample ranges of all tiles into their own accumulators;
+    the integer sum of the accumulators + rt_accum_to_frame is the single-render frame."""
+    import torch
+    from petershirleyraytracer_b200 import dist as rdist, scenes
+    c, r = book
+    W, H, spp, world = 96, 64, 10, 3
+    cam = scenes.book_camera(W, H)
+    p = rt.make_params(W, H, spp, 50, seed=4, early_out=False)
+    with rt.Scene(c, r) as sc:
+        full, sums, _ = rt.render(sc, cam, p, want_sums=True)
+        total = torch.zeros(H * W * 3, dtype=torch.int64, device="cuda")
+        for rank in range(world):
+            b, e = rdist.sample_range(spp, rank, world)
+            acc = torch.zeros(H * W * 3, dtype=torch.int64, device="cuda")
+            q = rt.make_params(W, H, e - b, 50, seed=4, early_out=False)
+            rt.render_pass_device(sc, cam, q, b, acc.data_ptr())
+            rt.render_finish(sc)
+            total += acc
+        frame = torch.empty(H * W * 4, dtype=torch.uint8, device="cuda")
+        rt.accum_to_frame(p, total.data_ptr(), spp, frame.data_ptr(), 0)
+        torch.cuda.synchronize()
+        single = rdist.render_sample_split(sc, cam, p, 0, 1)
+        torch.cuda.synchronize()
+    assert np.array_equal(frame.cpu().numpy().reshape(H, W, 4), full)
+    assert np.array_equal(single.cpu().numpy(), full)
+    assert np.array_equal(total.cpu().numpy().astype(np.float64).reshape(H, W, 3) / 2.0**44, sums)
