@@ -182,9 +182,12 @@ def load_traffic(wl_name: str, kernel: str):
 class GpuBench:
     """One workload on this rank's GPU: device-timed legs and the host-buffer e2e leg."""
 
-    def __init__(self, wl, rt, torch, dist, world, rank, local):
+    def __init__(self, wl, rt, torch, dist, world, rank, local, deal="tiles"):
         self.wl, self.rt, self.torch, self.dist = wl, rt, torch, dist
         self.world, self.rank, self.local = world, rank, local
+        # how N ranks share one frame: "tiles" = 8x8 tiles dealt round-robin + all-gather of the 8-bit shards;
+        # "samples" = every rank traces all tiles for 1/N of the samples + integer all-reduce of the radiance sums
+        self.deal = deal if world > 1 else "tiles"
         self.dev = torch.device("cuda", local)
         self.W, self.H, self.spp, self.depth = wl["W"], wl["H"], wl["spp"], wl["depth"]
         self.cam = wl["cam"]
@@ -196,14 +199,31 @@ class GpuBench:
         self.gathered = torch.empty(world * layout.shard_bytes, dtype=torch.uint8, device=self.dev) if world > 1 else None
         self.samples_per_step = self.W * self.H * self.spp
         self.big = len(wl["radii"]) > 4080   # beyond the linear scan's constant bank: BVH only
+        if self.deal == "samples":
+            self.accum = torch.zeros(self.H * self.W * 3, dtype=torch.int64, device=self.dev)
+            self.s_begin, self.s_end = rank * self.spp // world, (rank + 1) * self.spp // world
 
     def params(self, scan_mode, early_out, spp=None):
+        if self.deal == "samples":
+            return self.rt.make_params(self.W, self.H, spp or self.spp, self.depth, seed=0, early_out=early_out, scan_mode=scan_mode)
         return self.rt.make_params(self.W, self.H, spp or self.spp, self.depth, seed=0, early_out=early_out, scan_mode=scan_mode,
                                    shard_rank=self.rank, shard_count=self.world)
 
     def step(self, p, scene=None):
         """One frame, device buffers only.  Returns the kernels launched."""
         rt, sc = self.rt, scene or self.scene
+        if self.deal == "samples":
+            import copy
+            total = p.spp
+            b, e = self.rank * total // self.world, (self.rank + 1) * total // self.world
+            q = copy.copy(p)
+            q.spp = max(e - b, 1)
+            self.accum.zero_()
+            if e > b:
+                rt.render_pass_device(sc, self.cam, q, b, self.accum.data_ptr(), 0, self.stream)
+            self.dist.all_reduce(self.accum)
+            rt.accum_to_frame(p, self.accum.data_ptr(), total, self.frame.data_ptr(), self.local, self.stream)
+            return 2
         if self.world == 1:
             rt.render_device(sc, self.cam, p, self.frame.data_ptr(), 0, self.stream)
             return 1
@@ -331,6 +351,8 @@ def main():
     ap.add_argument("--spp", type=int, default=None, help="override the workload's spp (quick checks; not the contract config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--deal", default=os.environ.get("RT_BENCH_DEAL", "tiles"), choices=["tiles", "samples"],
+                    help="N > 1: tiles dealt to the ranks + all-gather (default), or samples split + integer all-reduce")
     args = ap.parse_args()
     wl = workload(args.workload, args.spp)
 
@@ -354,7 +376,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     fma_per_s, _ = rt.measure_fp32_peak(local)
 
-    b = GpuBench(wl, rt, torch, dist, world, rank, local)
+    b = GpuBench(wl, rt, torch, dist, world, rank, local, deal=args.deal)
     head_mode = rt.SCAN_BVH if b.big else rt.SCAN_FILTERED
     head_name = "bvh" if b.big else "scan"
 
@@ -380,7 +402,7 @@ def main():
             names.append("c5")
         for name in names:
             owl = workload(name)
-            ob = GpuBench(owl, rt, torch, dist, world, rank, local)
+            ob = GpuBench(owl, rt, torch, dist, world, rank, local, deal=args.deal)
             mode = rt.SCAN_BVH if ob.big else rt.SCAN_FILTERED
             nst = 1 if name == "c5" else 2
             warm = ob.params(mode, False, spp=max(1, owl["spp"] // 64))      # (a short frame warms caches / clocks; the timed steps are full frames)
@@ -430,7 +452,8 @@ def main():
                "config": config_dict(wl, world),
                "notes": {"scan_mode": "4-wide BVH + tie grid (RT_SCAN_BVH)" if b.big else "linear cull scan (RT_SCAN_FILTERED)",
                          "early_out": False, "paths_per_lane": 1 if b.big else 2,
-                         "parallelism": f"tiles8x8 dealt to {world} GPU(s)" + (" + NCCL all-gather" if world > 1 else ""),
+                         "parallelism": (f"tiles8x8 dealt to {world} GPU(s)" + (" + NCCL all-gather" if world > 1 else "")) if b.deal == "tiles"
+                         else f"samples split over {world} GPUs + NCCL all-reduce of the integer radiance sums",
                          "l2": l2_note(wl, b.big), "value_with_exact_early_out": eo["value"]},
                "clocks": clocks, "e2e": e2e, "gpu_launches": head["launches"], "roofline": roofline,
                "cpu_baseline": cpu, "cpu_baseline_1thread": cpu1, "cpu_baseline_reference_build": cpu_own,

@@ -389,17 +389,17 @@ public:
     progressive_render& operator=(const progressive_render&) = delete;
     // Traces the next `samples` samples of every pixel into the device-resident sums (rt_accum_add: no allocation and no
     // host copy per pass; asynchronous).  current() fetches the frame when somebody wants to look at it.
-    void add(int samples) {
+    // want_stats waits for the pass and keeps its counters in current().stats.
+    void add(int samples, bool want_stats = false) {
         rt_params q = p_;
         q.spp = samples;
-        check(rt_accum_add(world_.handle(), &cam_, &q, accum_, nullptr));
+        check(rt_accum_add(world_.handle(), &cam_, &q, accum_, want_stats ? &frame_.stats : nullptr));
         fresh_ = false;
     }
     int samples_done() const { return rt_accum_samples(accum_); }
     const frame& current() {
         if (!fresh_) {
             check(rt_accum_frame(accum_, frame_.rgba.data()));
-            check(rt_render_finish(world_.handle(), &frame_.stats));   // counters of the last pass
             fresh_ = true;
         }
         return frame_;

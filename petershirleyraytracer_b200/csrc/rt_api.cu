@@ -5,6 +5,7 @@
 #include "rt_kernels.cuh"
 
 #include <cmath>
+#include <atomic>
 #include <mutex>
 #include <cstdio>
 #include <cstring>
@@ -49,11 +50,34 @@ struct DevBuf {  // scoped device allocation
 
 }  // namespace
 
+// Device scratch one render launch works in.  A scene owns one; a progressive accumulator owns a second one so that
+// consecutive passes can overlap on two streams (the tail of pass k hides behind the start of pass k+1).
+struct Scratch {
+    unsigned int* d_tile_counter = nullptr;   // work-queue head of the persistent warps
+    unsigned long long* d_stats = nullptr;
+    void* d_accum = nullptr; size_t accum_cap = 0;   // fixed-point radiance per tile pixel (+ chunk counters behind it)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaError_t create() {
+        cudaError_t e;
+        if ((e = cudaMalloc(&d_tile_counter, sizeof(unsigned int))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&d_stats, 16 * sizeof(unsigned long long))) != cudaSuccess) return e;
+        if ((e = cudaEventCreate(&ev0)) != cudaSuccess) return e;
+        return cudaEventCreate(&ev1);
+    }
+    void destroy() {
+        cudaFree(d_tile_counter); cudaFree(d_stats); cudaFree(d_accum);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        *this = Scratch();
+    }
+};
+
 struct rt_scene {
     int device = 0;
     int n = 0, npad = 0;
     int sm_count = 0;
     bool cull_ok = true;   // every sphere finite and of moderate magnitude: the FP32 cull is usable
+    uint64_t filt_generation = 0;     // version of d_filt (the constant bank caches the last one it was given)
     float4* d_filt = nullptr;
     double4* d_exact = nullptr;
     double* d_inv_r = nullptr;        // RN(1/r) per sphere
@@ -64,10 +88,7 @@ struct rt_scene {
     rt::TieGridHost tie;              // tie grid of the current sphere positions (rt_bvh.h)
     float4* d_sph32 = nullptr;        // FP32 {centre, |r|} per sphere (tie grid shell tests)
     int4* d_tie_cells = nullptr; size_t tie_cells_cap = 0;
-    unsigned int* d_tile_counter = nullptr;   // work-queue head of the persistent warps
-    unsigned long long* d_stats = nullptr;
-    void* d_accum = nullptr; size_t accum_cap = 0;   // fixed-point radiance per tile pixel (+ chunk counters behind it)
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    Scratch scr;                      // per-launch device scratch of this scene's renders
     // scratch for the host-buffer entry points (grow only)
     void* d_frame = nullptr; size_t frame_cap = 0;
     void* d_sum = nullptr;   size_t sum_cap = 0;
@@ -83,7 +104,12 @@ struct rt_accum {
     int W = 0, H = 0;
     int samples = 0;                          // samples per pixel accumulated so far
     unsigned long long* d_sums = nullptr;     // W*H*3, 20.44 fixed point, frame pixel order
-    uchar4* d_frame = nullptr;                // write_color over all samples so far (rewritten by every pass)
+    uchar4* d_frame = nullptr;                // write_color over all samples so far (made on demand by rt_accum_frame)
+    Scratch scr[2];                           // passes alternate between two scratch sets / streams
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    int passes = 0;
+    const rt_scene* last_scene[2] = {nullptr, nullptr};
+    int last_mode[2] = {0, 0};
 };
 
 namespace {
@@ -93,7 +119,13 @@ namespace {
 // constant-bank render on that device.
 struct ConstBankGuard {
     std::mutex mu;
-    cudaEvent_t last[64] = {};
+    struct Dev {
+        const void* owner = nullptr;     // scene whose cull array the bank holds ...
+        uint64_t generation = 0;         // ... and which version of it (rt_update_scene bumps it)
+        cudaEvent_t copied = nullptr;    // ... recorded behind the copy into the bank
+        cudaStream_t copy_stream = nullptr;
+        std::vector<std::pair<cudaStream_t, cudaEvent_t>> users;   // last constant-bank render per stream
+    } dev[64];
 } g_const_bank;
 
 float round_down_f32(double v) {
@@ -184,7 +216,9 @@ int grow(void** p, size_t* cap, size_t need) {
 }
 
 int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* d_rgba, void* d_sum,
-                  cudaStream_t stream, int sample_base = 0, void* d_frame_accum = nullptr, bool frame_order_out = false) {
+                  cudaStream_t stream, int sample_base = 0, void* d_frame_accum = nullptr, bool frame_order_out = false,
+                  Scratch* scratch = nullptr) {
+    Scratch& X = scratch ? *scratch : sc->scr;
     int mode = 0;
     int rc = resolve_scan_mode(sc, p->scan_mode, &mode);
     if (rc) return rc;
@@ -209,7 +243,7 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     a.tiles_local = (L.tiles_total - p->shard_rank + p->shard_count - 1) / p->shard_count;
     a.compact_out = p->shard_count > 1 && !frame_order_out;   // (rt_render_multi: shards store straight into one frame)
     a.out = (uchar4*)d_rgba; a.sum_out = (double*)d_sum;
-    a.unit_counter = sc->d_tile_counter; a.stats = sc->d_stats;
+    a.unit_counter = X.d_tile_counter; a.stats = X.d_stats;
     a.sample_base = sample_base; a.frame_accum = (unsigned long long*)d_frame_accum;
 
     int R = p->reserved[0];
@@ -219,16 +253,26 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     // cull array source: constant bank (default; FFMAs then read a uniform-register operand) or the
     // TMA-staged shared-memory copy (reserved[2] == 1), kept for A/B evidence
     const bool use_const = p->reserved[2] != 1 && mode == RT_SCAN_FILTERED;
-    // One critical section from the wait on the previous constant-bank render through this render's launch and
+    // One critical section from the wait on the previous constant-bank renders through this render's launch and
     // event record: a second host thread rendering another FILTERED scene on another stream of this device then
-    // queues its copy into the bank strictly behind this kernel (and not between this copy and this launch).
+    // queues its copy into the bank strictly behind this kernel (and not between this copy and this launch).  Renders
+    // of the scene whose array the bank already holds need neither the copy nor the wait (they may overlap).
     std::unique_lock<std::mutex> bank_lock;
     if (use_const) {
         bank_lock = std::unique_lock<std::mutex>(g_const_bank.mu);
-        cudaEvent_t& prev = g_const_bank.last[sc->device & 63];
-        if (prev) RT_CUDA(cudaStreamWaitEvent(stream, prev, 0));
-        RT_CUDA(cudaMemcpyToSymbolAsync(rt::c_filt, sc->d_filt, (size_t)(sc->npad + rt::kScanPad) * sizeof(float4), 0,
-                                        cudaMemcpyDeviceToDevice, stream));
+        ConstBankGuard::Dev& B = g_const_bank.dev[sc->device & 63];
+        if (B.owner != sc || B.generation != sc->filt_generation) {
+            for (auto& u : B.users) RT_CUDA(cudaStreamWaitEvent(stream, u.second, 0));
+            RT_CUDA(cudaMemcpyToSymbolAsync(rt::c_filt, sc->d_filt, (size_t)(sc->npad + rt::kScanPad) * sizeof(float4), 0,
+                                            cudaMemcpyDeviceToDevice, stream));
+            // (the events stay in the list: a later copy by another scene must still wait for those kernels; entries of
+            //  this stream are overwritten below)
+            if (!B.copied) RT_CUDA(cudaEventCreateWithFlags(&B.copied, cudaEventDisableTiming));
+            RT_CUDA(cudaEventRecord(B.copied, stream));
+            B.owner = sc; B.generation = sc->filt_generation; B.copy_stream = stream;
+        } else if (stream != B.copy_stream) {
+            RT_CUDA(cudaStreamWaitEvent(stream, B.copied, 0));   // the bank is this scene's once that copy has run
+        }
     }
     rt::RenderSmem S = rt::render_smem(use_const ? 0 : a.sc.npad, R);
     void (*kern)(const rt::RenderArgs) = nullptr;
@@ -261,38 +305,43 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     if (a.chunks > 1) {
         const size_t acc_bytes = (size_t)a.tiles_local * rt::kTilePix * 3 * sizeof(unsigned long long);
         const size_t done_bytes = (size_t)a.tiles_local * sizeof(unsigned int);
-        int rc2 = grow(&sc->d_accum, &sc->accum_cap, acc_bytes + done_bytes);
+        int rc2 = grow(&X.d_accum, &X.accum_cap, acc_bytes + done_bytes);
         if (rc2) return rc2;
-        a.accum = (unsigned long long*)sc->d_accum;
-        a.tile_done = (unsigned int*)((char*)sc->d_accum + acc_bytes);
-        RT_CUDA(cudaMemsetAsync(sc->d_accum, 0, acc_bytes + done_bytes, stream));
+        a.accum = (unsigned long long*)X.d_accum;
+        a.tile_done = (unsigned int*)((char*)X.d_accum + acc_bytes);
+        RT_CUDA(cudaMemsetAsync(X.d_accum, 0, acc_bytes + done_bytes, stream));
     }
-    RT_CUDA(cudaMemsetAsync(sc->d_tile_counter, 0, sizeof(unsigned int), stream));
-    RT_CUDA(cudaMemsetAsync(sc->d_stats, 0, rt::kNumStats * sizeof(unsigned long long), stream));
+    RT_CUDA(cudaMemsetAsync(X.d_tile_counter, 0, sizeof(unsigned int), stream));
+    RT_CUDA(cudaMemsetAsync(X.d_stats, 0, rt::kNumStats * sizeof(unsigned long long), stream));
     if (a.compact_out && d_rgba) RT_CUDA(cudaMemsetAsync(d_rgba, 0, (size_t)L.shard_bytes, stream));
-    RT_CUDA(cudaEventRecord(sc->ev0, stream));
+    RT_CUDA(cudaEventRecord(X.ev0, stream));
     kern<<<grid, rt::kThreads, S.total, stream>>>(a);
     RT_CUDA(cudaGetLastError());
-    RT_CUDA(cudaEventRecord(sc->ev1, stream));
+    RT_CUDA(cudaEventRecord(X.ev1, stream));
     if (use_const) {
-        cudaEvent_t& prev = g_const_bank.last[sc->device & 63];
-        if (!prev) RT_CUDA(cudaEventCreateWithFlags(&prev, cudaEventDisableTiming));
-        RT_CUDA(cudaEventRecord(prev, stream));
+        ConstBankGuard::Dev& B = g_const_bank.dev[sc->device & 63];
+        cudaEvent_t ev = nullptr;
+        for (auto& u : B.users) if (u.first == stream) ev = u.second;
+        if (!ev) {
+            RT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            B.users.push_back({stream, ev});
+        }
+        RT_CUDA(cudaEventRecord(ev, stream));
         bank_lock.unlock();
     }
-    sc->pending = true; sc->last_stream = stream; sc->last_mode = mode; sc->last_launches = 1;
+    if (!scratch) { sc->pending = true; sc->last_stream = stream; sc->last_mode = mode; sc->last_launches = 1; }
     return RT_OK;
 }
 
 int finish_render(rt_scene* sc, rt_stats* st) {
     if (!sc->pending) return fail(RT_ERR_INVALID, "no render in flight on this scene");
-    RT_CUDA(cudaEventSynchronize(sc->ev1));
+    RT_CUDA(cudaEventSynchronize(sc->scr.ev1));
     sc->pending = false;
     if (!st) return RT_OK;
     unsigned long long h[rt::kNumStats];
-    RT_CUDA(cudaMemcpy(h, sc->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+    RT_CUDA(cudaMemcpy(h, sc->scr.d_stats, sizeof h, cudaMemcpyDeviceToHost));
     float ms = 0.f;
-    RT_CUDA(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1));
+    RT_CUDA(cudaEventElapsedTime(&ms, sc->scr.ev0, sc->scr.ev1));
     std::memset(st, 0, sizeof *st);
     st->kernel_ms = ms;
     st->samples = h[rt::ST_SAMPLES]; st->casts = h[rt::ST_CASTS];
@@ -322,6 +371,8 @@ int fill_scene(rt_scene* sc, const double* centres_xyz, const double* radii, boo
     std::vector<double4> exact((size_t)n > 0 ? n : 1);
     std::vector<double> inv_r((size_t)n > 0 ? n : 1);
     sc->cull_ok = true;
+    static std::atomic<uint64_t> next_generation{1};
+    sc->filt_generation = next_generation++;   // (unique across scenes: a freed scene's address may be reused)
     for (int k = 0; k < sc->npad + rt::kScanPad; ++k) {
         float4 f;
         if (k < n) {
@@ -339,6 +390,10 @@ int fill_scene(rt_scene* sc, const double* centres_xyz, const double* radii, boo
         }
         filt[k] = f;
     }
+    std::vector<float4> sph((size_t)n > 0 ? n : 1);   // FP32 {centre, |r|}: shell pre-tests (rt_device.cuh: tie_candidate)
+    for (int k = 0; k < n; ++k)
+        sph[k] = make_float4((float)centres_xyz[3 * k], (float)centres_xyz[3 * k + 1], (float)centres_xyz[3 * k + 2], (float)std::fabs(radii[k]));
+    if (cudaMemcpy(sc->d_sph32, sph.data(), sph.size() * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess) return RT_ERR_CUDA;
     if (cudaMemcpy(sc->d_filt, filt.data(), filt.size() * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(sc->d_exact, exact.data(), exact.size() * sizeof(double4), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(sc->d_inv_r, inv_r.data(), inv_r.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
@@ -378,9 +433,7 @@ int fill_scene(rt_scene* sc, const double* centres_xyz, const double* radii, boo
             if (cudaMalloc(&sc->d_tie_cells, cb) != cudaSuccess) return RT_ERR_CUDA;
             sc->tie_cells_cap = cb;
         }
-        if (cudaMemcpy(sc->d_tie_cells, sc->tie.cells.data(), cb, cudaMemcpyHostToDevice) != cudaSuccess ||
-            cudaMemcpy(sc->d_sph32, sc->tie.sph.data(), (size_t)(n > 0 ? n : 1) * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess)
-            return RT_ERR_CUDA;
+        if (cudaMemcpy(sc->d_tie_cells, sc->tie.cells.data(), cb, cudaMemcpyHostToDevice) != cudaSuccess) return RT_ERR_CUDA;
     }
     return RT_OK;
 }
@@ -437,9 +490,7 @@ int rt_upload_scene(const double* centres_xyz, const double* radii, int32_t n, i
             cudaMalloc(&sc->d_exact, ne * sizeof(double4)) != cudaSuccess ||
             cudaMalloc(&sc->d_inv_r, ne * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&sc->d_sph32, ne * sizeof(float4)) != cudaSuccess ||
-            cudaMalloc(&sc->d_tile_counter, sizeof(unsigned int)) != cudaSuccess ||
-            cudaMalloc(&sc->d_stats, rt::kNumStats * sizeof(unsigned long long)) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
-        if (cudaEventCreate(&sc->ev0) != cudaSuccess || cudaEventCreate(&sc->ev1) != cudaSuccess) { rc = RT_ERR_CUDA; break; }
+            sc->scr.create() != cudaSuccess) { rc = RT_ERR_CUDA; break; }
         rc = fill_scene(sc, centres_xyz, radii, /*refit=*/false);
     } while (0);
     if (rc != RT_OK) {
@@ -456,12 +507,8 @@ int rt_update_scene(rt_scene* sc, const double* centres_xyz, const double* radii
     if (n != sc->n) return fail(RT_ERR_INVALID, "rt_update_scene keeps the sphere count; upload a new scene to change it");
     DeviceGuard guard(sc->device);
     if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
-    if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->ev1));  // (rt_render_finish can still read that render's counters)
-    {   // a constant-bank render of the old cull array may still be queued on another stream of this device
-        std::lock_guard<std::mutex> lock(g_const_bank.mu);
-        cudaEvent_t prev = g_const_bank.last[sc->device & 63];
-        if (prev) RT_CUDA(cudaEventSynchronize(prev));
-    }
+    if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->scr.ev1));  // (rt_render_finish can still read that render's counters)
+    RT_CUDA(cudaDeviceSynchronize());   // renders of the old arrays may still be queued on other streams of this device
     const int rc = fill_scene(sc, centres_xyz, radii, refit != 0);
     if (rc != RT_OK) return fail(rc, std::string("scene update: ") + cudaGetErrorString(cudaGetLastError()));
     return RT_OK;
@@ -470,12 +517,11 @@ int rt_update_scene(rt_scene* sc, const double* centres_xyz, const double* radii
 void rt_free_scene(rt_scene* sc) {
     if (!sc) return;
     DeviceGuard guard(sc->device);
-    if (sc->pending) cudaEventSynchronize(sc->ev1);
-    cudaFree(sc->d_filt); cudaFree(sc->d_exact); cudaFree(sc->d_inv_r); cudaFree(sc->d_tile_counter); cudaFree(sc->d_stats);
+    if (sc->pending) cudaEventSynchronize(sc->scr.ev1);
+    cudaFree(sc->d_filt); cudaFree(sc->d_exact); cudaFree(sc->d_inv_r);
     cudaFree(sc->d_bvh_nodes); cudaFree(sc->d_bvh_leaf); cudaFree(sc->d_sph32); cudaFree(sc->d_tie_cells);
-    cudaFree(sc->d_frame); cudaFree(sc->d_sum); cudaFree(sc->d_accum);
-    if (sc->ev0) cudaEventDestroy(sc->ev0);
-    if (sc->ev1) cudaEventDestroy(sc->ev1);
+    cudaFree(sc->d_frame); cudaFree(sc->d_sum);
+    sc->scr.destroy();
     delete sc;
 }
 
@@ -497,7 +543,7 @@ int rt_render_device(const rt_scene* scene, const rt_camera* cam, const rt_param
     rt_scene* sc = const_cast<rt_scene*>(scene);
     DeviceGuard guard(sc->device);
     if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
-    if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->ev1));
+    if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->scr.ev1));
     if (d_sum && p->shard_count > 1) return fail(RT_ERR_INVALID, "radiance sums are only available for shard_count == 1");
     return launch_render(sc, cam, p, d_rgba, d_sum, (cudaStream_t)stream);
 }
@@ -517,7 +563,7 @@ int rt_render_pass_device(const rt_scene* scene, const rt_camera* cam, const rt_
     rt_scene* sc = const_cast<rt_scene*>(scene);
     DeviceGuard guard(sc->device);
     if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
-    if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->ev1));
+    if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->scr.ev1));
     return launch_render(sc, cam, p, d_rgba, nullptr, (cudaStream_t)stream, sample_begin, d_accum);
 }
 
@@ -546,6 +592,29 @@ int rt_render_pass(const rt_scene* scene, const rt_camera* cam, const rt_params*
 }
 
 // ---- device-resident progressive accumulator (no allocation, no host copy per pass)
+static int read_stats(const Scratch& X, int n_spheres, int mode, rt_stats* st) {
+    unsigned long long h[rt::kNumStats];
+    RT_CUDA(cudaMemcpy(h, X.d_stats, sizeof h, cudaMemcpyDeviceToHost));
+    float ms = 0.f;
+    RT_CUDA(cudaEventElapsedTime(&ms, X.ev0, X.ev1));
+    std::memset(st, 0, sizeof *st);
+    st->kernel_ms = ms;
+    st->samples = h[rt::ST_SAMPLES]; st->casts = h[rt::ST_CASTS];
+    st->sphere_tests = (mode == RT_SCAN_FILTERED) ? h[rt::ST_CASTS] * (uint64_t)n_spheres : 0;
+    st->node_tests = rt::kBvhWidth * h[rt::ST_NODE_TESTS];
+    st->exact_tests = h[rt::ST_EXACT_TESTS];
+    st->black = h[rt::ST_BLACK]; st->early_outs = h[rt::ST_EARLY_OUTS];
+    st->primary_hits = h[rt::ST_PRIMARY_HITS]; st->overflows = h[rt::ST_OVERFLOWS];
+    st->self_resolved = h[rt::ST_SELF_RESOLVED];
+    st->launches = 1;
+    return RT_OK;
+}
+
+static int accum_sync(const rt_accum* a) {   // every pass launched so far has finished
+    for (int i = 0; i < 2; ++i) if (a->stream[i]) RT_CUDA(cudaStreamSynchronize(a->stream[i]));
+    return RT_OK;
+}
+
 int rt_accum_create(int32_t width, int32_t height, int32_t device, rt_accum** out) {
     if (!out) return fail(RT_ERR_INVALID, "out is NULL");
     *out = nullptr;
@@ -556,13 +625,15 @@ int rt_accum_create(int32_t width, int32_t height, int32_t device, rt_accum** ou
     if (!a) return fail(RT_ERR_NOMEM, "host allocation failed");
     a->device = device; a->W = width; a->H = height;
     const size_t npix = (size_t)width * height;
-    if (cudaMalloc(&a->d_sums, npix * 3 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMalloc(&a->d_frame, npix * sizeof(uchar4)) != cudaSuccess ||
-        cudaMemset(a->d_sums, 0, npix * 3 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(a->d_frame, 0, npix * sizeof(uchar4)) != cudaSuccess) {
+    bool ok = cudaMalloc(&a->d_sums, npix * 3 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc(&a->d_frame, npix * sizeof(uchar4)) == cudaSuccess &&
+              cudaMemset(a->d_sums, 0, npix * 3 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMemset(a->d_frame, 0, npix * sizeof(uchar4)) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+        ok = a->scr[i].create() == cudaSuccess && cudaStreamCreateWithFlags(&a->stream[i], cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) {
         const std::string msg = std::string("rt_accum_create: ") + cudaGetErrorString(cudaGetLastError());
-        cudaFree(a->d_sums); cudaFree(a->d_frame);
-        delete a;
+        rt_accum_destroy(a);
         return fail(RT_ERR_CUDA, msg);
     }
     *out = a;
@@ -572,7 +643,10 @@ int rt_accum_create(int32_t width, int32_t height, int32_t device, rt_accum** ou
 void rt_accum_destroy(rt_accum* a) {
     if (!a) return;
     DeviceGuard guard(a->device);
-    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) {
+        if (a->stream[i]) { cudaStreamSynchronize(a->stream[i]); cudaStreamDestroy(a->stream[i]); }
+        a->scr[i].destroy();
+    }
     cudaFree(a->d_sums); cudaFree(a->d_frame);
     delete a;
 }
@@ -583,11 +657,16 @@ int rt_accum_reset(rt_accum* a) {
     if (!a) return fail(RT_ERR_INVALID, "NULL accumulator");
     DeviceGuard guard(a->device);
     if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
-    RT_CUDA(cudaMemsetAsync(a->d_sums, 0, (size_t)a->W * a->H * 3 * sizeof(unsigned long long), nullptr));
+    int rc = accum_sync(a);
+    if (rc) return rc;
+    RT_CUDA(cudaMemset(a->d_sums, 0, (size_t)a->W * a->H * 3 * sizeof(unsigned long long)));
     a->samples = 0;
     return RT_OK;
 }
 
+// Consecutive passes alternate between two streams (each with its own scratch), so the ramp-down of pass k -- the last
+// work units finishing on a few SMs -- overlaps the start of pass k+1; the integer sums are added atomically and do
+// not depend on the order.  (In RT_SCAN_FILTERED mode both streams share the scene's cull array in the constant bank.)
 int rt_accum_add(const rt_scene* scene, const rt_camera* cam, const rt_params* p, rt_accum* acc, rt_stats* st) {
     if (!scene || !cam || !acc) return fail(RT_ERR_INVALID, "NULL argument");
     int rc = check_params(p);
@@ -600,18 +679,36 @@ int rt_accum_add(const rt_scene* scene, const rt_camera* cam, const rt_params* p
         return fail(RT_ERR_INVALID, "at most 2^20 samples per pixel in one accumulator (radiance sums are 20.44 fixed point)");
     DeviceGuard guard(sc->device);
     if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
-    if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->ev1));
-    rc = launch_render(sc, cam, p, acc->d_frame, nullptr, nullptr, acc->samples, acc->d_sums);
+    if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->scr.ev1));   // (a render through the scene's own entry points)
+    const int slot = acc->passes & 1;
+    int mode = 0;
+    rc = resolve_scan_mode(sc, p->scan_mode, &mode);
     if (rc) return rc;
+    rc = launch_render(sc, cam, p, nullptr, nullptr, acc->stream[slot], acc->samples, acc->d_sums, false, &acc->scr[slot]);
+    if (rc) return rc;
+    acc->passes += 1;
     acc->samples += p->spp;
-    return st ? finish_render(sc, st) : RT_OK;   // without stats the pass stays asynchronous
+    acc->last_scene[slot] = sc; acc->last_mode[slot] = mode;
+    if (!st) return RT_OK;                       // without stats the pass stays asynchronous
+    RT_CUDA(cudaEventSynchronize(acc->scr[slot].ev1));
+    return read_stats(acc->scr[slot], sc->n, mode, st);
 }
 
 int rt_accum_frame(const rt_accum* a, uint8_t* rgba_out) {
     if (!a || !rgba_out) return fail(RT_ERR_INVALID, "NULL argument");
     DeviceGuard guard(a->device);
     if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
-    RT_CUDA(cudaMemcpy(rgba_out, a->d_frame, (size_t)a->W * a->H * 4, cudaMemcpyDeviceToHost));   // (ordered behind the passes)
+    int rc = accum_sync(a);
+    if (rc) return rc;
+    const size_t npix = (size_t)a->W * a->H;
+    if (a->samples > 0) {   // write_color (programs/color.h:16-23) over all samples so far
+        int grid = (int)((npix + 255) / 256);
+        if (grid > 148 * 16) grid = 148 * 16;
+        rt::accum_to_frame_kernel<<<grid, 256, 0, a->stream[0]>>>(a->d_sums, a->d_frame, npix, a->samples);
+        RT_CUDA(cudaGetLastError());
+        RT_CUDA(cudaStreamSynchronize(a->stream[0]));
+    }
+    RT_CUDA(cudaMemcpy(rgba_out, a->d_frame, npix * 4, cudaMemcpyDeviceToHost));
     return RT_OK;
 }
 
@@ -619,6 +716,8 @@ int rt_accum_read(const rt_accum* a, uint64_t* sums_out) {
     if (!a || !sums_out) return fail(RT_ERR_INVALID, "NULL argument");
     DeviceGuard guard(a->device);
     if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    int rc = accum_sync(a);
+    if (rc) return rc;
     RT_CUDA(cudaMemcpy(sums_out, a->d_sums, (size_t)a->W * a->H * 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return RT_OK;
 }
@@ -627,6 +726,8 @@ int rt_accum_write(rt_accum* a, const uint64_t* sums, int32_t samples_done) {
     if (!a || !sums || samples_done < 0 || samples_done > (1 << 20)) return fail(RT_ERR_INVALID, "bad argument");
     DeviceGuard guard(a->device);
     if (!guard.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    int rc = accum_sync(a);
+    if (rc) return rc;
     RT_CUDA(cudaMemcpy(a->d_sums, sums, (size_t)a->W * a->H * 3 * sizeof(unsigned long long), cudaMemcpyHostToDevice));
     a->samples = samples_done;
     return RT_OK;
@@ -686,7 +787,7 @@ int rt_render_multi(rt_scene* const* scenes, int32_t n_scenes, const rt_camera* 
         rt_scene* sc = scenes[i];
         DeviceGuard g(sc->device);
         if (!g.ok) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
-        if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->ev1));
+        if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->scr.ev1));
         q.shard_rank = i;
         if (peer_ok) {
             rc = launch_render(sc, cam, &q, sc0->d_frame, nullptr, nullptr, 0, nullptr, /*frame_order_out=*/true);
@@ -755,7 +856,7 @@ int rt_render(const rt_scene* scene, const rt_camera* cam, const rt_params* p, u
     rc = grow(&sc->d_frame, &sc->frame_cap, npix * 4);
     if (rc) return rc;
     if (sum_out) { rc = grow(&sc->d_sum, &sc->sum_cap, npix * 3 * sizeof(double)); if (rc) return rc; }
-    if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->ev1));
+    if (sc->pending) RT_CUDA(cudaEventSynchronize(sc->scr.ev1));
     rc = launch_render(sc, cam, p, sc->d_frame, sum_out ? sc->d_sum : nullptr, nullptr);
     if (rc) return rc;
     rc = finish_render(sc, st);
@@ -864,14 +965,14 @@ static int ray_color_impl(const rt_scene* scene, const double* org, const double
     RT_CUDA(d_org.alloc(3 * (size_t)nrays)); RT_CUDA(d_dir.alloc(3 * (size_t)nrays)); RT_CUDA(d_rgb.alloc(3 * (size_t)nrays));
     RT_CUDA(cudaMemcpy(d_org.p, org, 3 * (size_t)nrays * sizeof(double), cudaMemcpyHostToDevice));
     RT_CUDA(cudaMemcpy(d_dir.p, dir, 3 * (size_t)nrays * sizeof(double), cudaMemcpyHostToDevice));
-    RT_CUDA(cudaMemset(sc->d_stats, 0, rt::kNumStats * sizeof(unsigned long long)));
+    RT_CUDA(cudaMemset(sc->scr.d_stats, 0, rt::kNumStats * sizeof(unsigned long long)));
     rt::RayBatchArgs a;
     std::memset(&a, 0, sizeof a);
     a.sc = scene_dev(sc, mode); a.org = d_org.p; a.dir = d_dir.p; a.nrays = nrays; a.scan_mode = mode;
     a.tmin = tmin; a.sh = sh;
     a.depth = depth; a.early_out = (early_out && tmin == 0.0) ? 1 : 0;  // the cut is only exact for tmin == 0
     a.key0 = (uint32_t)seed; a.key1 = (uint32_t)(seed >> 32);
-    a.rgb_out = d_rgb.p; a.stats = sc->d_stats;
+    a.rgb_out = d_rgb.p; a.stats = sc->scr.d_stats;
     const rt::BatchSmem S = rt::batch_smem(a.sc.npad);
     RT_CUDA(cudaFuncSetAttribute(rt::ray_color_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
     rt::ray_color_kernel<<<batch_grid(sc, nrays), rt::kThreads, S.total>>>(a);
@@ -880,7 +981,7 @@ static int ray_color_impl(const rt_scene* scene, const double* org, const double
     RT_CUDA(cudaMemcpy(rgb_out, d_rgb.p, 3 * (size_t)nrays * sizeof(double), cudaMemcpyDeviceToHost));
     if (st) {
         unsigned long long h[rt::kNumStats];
-        RT_CUDA(cudaMemcpy(h, sc->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+        RT_CUDA(cudaMemcpy(h, sc->scr.d_stats, sizeof h, cudaMemcpyDeviceToHost));
         st->samples = h[rt::ST_SAMPLES]; st->casts = h[rt::ST_CASTS]; st->exact_tests = h[rt::ST_EXACT_TESTS];
         st->sphere_tests = mode == RT_SCAN_FILTERED ? h[rt::ST_CASTS] * (uint64_t)sc->n : 0;
         st->black = h[rt::ST_BLACK]; st->early_outs = h[rt::ST_EARLY_OUTS]; st->primary_hits = h[rt::ST_PRIMARY_HITS];

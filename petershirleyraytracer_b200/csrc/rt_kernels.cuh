@@ -87,10 +87,10 @@ __device__ __forceinline__ void finalize_tile(const RenderArgs& a, int tile_l, c
         if (kFromGlobal) { v0 = __ldcg(src + p * 3); v1 = __ldcg(src + p * 3 + 1); v2 = __ldcg(src + p * 3 + 2); }
         else { v0 = src[p * 3]; v1 = src[p * 3 + 1]; v2 = src[p * 3 + 2]; }
         const size_t frame_idx = (size_t)(g.y0 + ly) * a.W + (g.x0 + lx);
-        if (a.frame_accum) {  // progressive pass: integer sums continue from the earlier passes (order-independent)
+        if (a.frame_accum) {  // progressive pass: integer sums continue from the earlier passes (order-independent;
+                              // atomic because two passes of one accumulator may be in flight, rt_accum_add)
             unsigned long long* fa = a.frame_accum + frame_idx * 3;
-            v0 += fa[0]; v1 += fa[1]; v2 += fa[2];
-            fa[0] = v0; fa[1] = v1; fa[2] = v2;
+            v0 += atomicAdd(fa + 0, v0); v1 += atomicAdd(fa + 1, v1); v2 += atomicAdd(fa + 2, v2);
         }
         const double sr = __ull2double_rn(v0) * inv_fs, sg = __ull2double_rn(v1) * inv_fs, sb = __ull2double_rn(v2) * inv_fs;
         uchar4 q;
@@ -393,6 +393,10 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R>::kMinBlocks) render_
 #define RT_WAVE_REGEN 24
 #endif
 constexpr int kPool = RT_WAVE_POOL;        // path records per warp
+#ifndef RT_WAVE_FETCH
+#define RT_WAVE_FETCH 8
+#endif
+constexpr int kFetchMin = RT_WAVE_FETCH;   // T phase: idle lanes take new rays in batches of at least this many
 constexpr int kRegenMin = RT_WAVE_REGEN;   // free records are refilled in batches of at least this many (a regeneration
                                            // round costs the same for 2 lanes as for 32), so (kPool - kRegenMin) / 2 >= 32
                                            // keeps both phases at full width
@@ -557,26 +561,18 @@ __global__ void __launch_bounds__(kThreads, RT_WAVE_MINB) render_wave_kernel(con
                 const int depth = (int)(mt.w & 0xffffu), lp = (int)(mt.w >> 16);  // lp: bits 0-5 pixel in tile, bit 6 buffer
                 buf = lp >> 6;
                 const int bounces = a.max_depth - depth;
-                const double A = ddot(dx, dy, dz, dx, dy, dz);  // programs/sphere.cc:9
-                const int kk = bk[rec];
+                const int kk = bk[rec];   // (a hit: misses end in the T phase)
                 ++n_casts;
-                if (kk < 0) {
-                    // miss: sky (programs/main.cc:46-48) * attenuation -> fixed-point accumulate
-                    double cr, cg, cb;
-                    sky_color(a.sh, dy, A, bounces, cr, cg, cb);
-                    const double fs = (double)(1ull << kFixShift);
-                    unsigned long long* ap = acc + (buf * kTilePix + (lp & 63)) * 3;
-                    fixed_add(ap + 0, __double2ull_rz(cr * fs));
-                    fixed_add(ap + 1, __double2ull_rz(cg * fs));
-                    fixed_add(ap + 2, __double2ull_rz(cb * fs));
-                    dest = 3;
-                } else {
+                {
                     Best hitb;
                     hitb.t = bt[rec]; hitb.k = kk & 0x3fffffff; hitb.C = (kk >> 30) & 1 ? 0.0 : 1.0;
                     if (bounces == 0) ++n_primary;
                     if (a.early_out && hitb.t == 0.0 && hitb.C == 0.0) {
                         // origin stays on this sphere with C == 0: every later cast hits at t == 0 -> black
                         ++n_early; ++n_black;
+                        dest = 3;
+                    } else if (depth == 0) {  // programs/main.cc:36-37: the next ray_color call has depth < 0 -> black
+                        ++n_black;
                         dest = 3;
                     } else {
                         const Record rc = make_record(a.sc, hitb, ox, oy, oz, dx, dy, dz);
@@ -586,10 +582,7 @@ __global__ void __launch_bounds__(kThreads, RT_WAVE_MINB) render_wave_kernel(con
                         const double ndx = dsub(dadd(dadd(rc.px, rc.nx), rx), rc.px);
                         const double ndy = dsub(dadd(dadd(rc.py, rc.ny), ry), rc.py);
                         const double ndz = dsub(dadd(dadd(rc.pz, rc.nz), rz), rc.pz);
-                        if (depth == 0) {  // programs/main.cc:36-37: the next ray_color call has depth < 0
-                            ++n_black;
-                            dest = 3;
-                        } else {
+                        {
                             st[0 * kPool + rec] = rc.px; st[1 * kPool + rec] = rc.py; st[2 * kPool + rec] = rc.pz;
                             st[3 * kPool + rec] = ndx; st[4 * kPool + rec] = ndy; st[5 * kPool + rec] = ndz;
                             mt.w = (uint32_t)(depth - 1) | ((uint32_t)lp << 16);
@@ -620,33 +613,79 @@ __global__ void __launch_bounds__(kThreads, RT_WAVE_MINB) render_wave_kernel(con
             infl1 -= __popc(mB); infl0 -= __popc(mF) - __popc(mB);
         } else {
             // ================= T: BVH traversal bounded by the start sphere's hit
-            const int m = min(nT, 32);
-            const bool active = lane < m;
-            const int rec = active ? (int)qT[nT - m + lane] : 0;
-            nT -= m;
-            if (active) {
-                const double ox = st[0 * kPool + rec], oy = st[1 * kPool + rec], oz = st[2 * kPool + rec];
-                const double dx = st[3 * kPool + rec], dy = st[4 * kPool + rec], dz = st[5 * kPool + rec];
-                const double A = ddot(dx, dy, dz, dx, dy, dz);
-                const int kk = bk[rec];
-                Best best;
-                best.t = bt[rec]; best.k = kk < 0 ? -1 : (kk & 0x3fffffff); best.C = (kk >= 0 && ((kk >> 30) & 1)) ? 0.0 : 1.0;
-                const bool sane = A > 0.0 && A < kInf && (ox * ox + oy * oy + oz * oz) < kCullMaxMag2;
-                bool seq = !(sane && a.tmin >= 0.0);   // such rays take the sequential FP64 scan
-                if (!seq) {
-                    bool deep = false;
-                    bvh_cast(a.sc, ox, oy, oz, dx, dy, dz, A, a.tmin, kInf, best, selfk[rec], n_exact, n_nodes, deep);
-                    seq = deep;   // traversal stack exhausted (degenerate tree) / FP32-denormal direction component
+            // Lanes take records from the T queue, traverse one wide node per iteration, and a lane whose ray is done
+            // hands in its result (hit -> S queue; miss -> sky colour, record freed) and takes the next record while
+            // the others keep going: the traversal loop stays full although rays visit 1 to 15 nodes.  (Fetching is
+            // batched -- kFetchMin idle lanes -- because the per-ray setup is ~100 instructions.)
+            int rec = -1, skip = -1, state = 0;
+            double ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1;
+            Best best;
+            best.t = kInf; best.C = 1.0; best.k = -1;
+            RcpA dA = make_rcp(1.0);
+            BvhTrav T;
+            T.node = 0; T.sp = 0;
+            for (;;) {
+                const unsigned idle = __ballot_sync(0xffffffffu, rec < 0);
+                if (nT > 0 && __popc(idle) >= kFetchMin) {
+                    const int rank = __popc(idle & lt_mask);
+                    if (rec < 0 && rank < nT) {
+                        rec = (int)qT[nT - 1 - rank];
+                        ox = st[0 * kPool + rec]; oy = st[1 * kPool + rec]; oz = st[2 * kPool + rec];
+                        dx = st[3 * kPool + rec]; dy = st[4 * kPool + rec]; dz = st[5 * kPool + rec];
+                        const double A = ddot(dx, dy, dz, dx, dy, dz);
+                        const int kk = bk[rec];
+                        best.t = bt[rec]; best.k = kk < 0 ? -1 : (kk & 0x3fffffff); best.C = (kk >= 0 && ((kk >> 30) & 1)) ? 0.0 : 1.0;
+                        skip = selfk[rec];
+                        dA = make_rcp(A);
+                        const bool sane = A > 0.0 && A < kInf && (ox * ox + oy * oy + oz * oz) < kCullMaxMag2;
+                        state = 0;
+                        if (!(sane && a.tmin >= 0.0) || !bvh_setup(T, ox, oy, oz, dx, dy, dz, best.k >= 0 ? best.t : kInf)) state = 2;
+                    }
+                    nT -= min(__popc(idle), nT);
                 }
-                if (seq) {
+                if (__ballot_sync(0xffffffffu, rec >= 0) == 0u) break;
+                if (rec >= 0 && state == 0)
+                    state = bvh_step(a.sc, T, ox, oy, oz, dx, dy, dz, dA, a.tmin, kInf, best, skip, n_exact, n_nodes);
+                if (rec >= 0 && state == 2) {   // not traversable / stack exhausted: the sequential FP64 scan (rare)
                     ++n_ovf;
-                    full_scan_cold(a.sc, ox, oy, oz, dx, dy, dz, A, a.tmin, &best, &n_exact);
+                    full_scan_cold(a.sc, ox, oy, oz, dx, dy, dz, dA.A, a.tmin, &best, &n_exact);
+                    state = 1;
                 }
-                bt[rec] = best.t;
-                bk[rec] = best.k < 0 ? -1 : (best.k | (best.C == 0.0 ? (1 << 30) : 0));
-                qS[nS + lane] = (uint8_t)rec;
+                const unsigned fin = __ballot_sync(0xffffffffu, rec >= 0 && state == 1);
+                if (fin) {
+                    int dest = 0, buf = 0;
+                    if (rec >= 0 && state == 1) {
+                        if (best.k < 0) {
+                            // miss: the path ends here with the sky colour (programs/main.cc:46-48) times its attenuation
+                            // -> fixed-point accumulate.  (In this phase a third of the finishing lanes miss; in S one
+                            // record in 24 would.)
+                            const uint4 mt = meta[rec];
+                            const int depth = (int)(mt.w & 0xffffu), lp = (int)(mt.w >> 16);
+                            buf = lp >> 6;
+                            ++n_casts;
+                            double cr, cg, cb;
+                            sky_color(a.sh, dy, dA.A, a.max_depth - depth, cr, cg, cb);
+                            const double fs = (double)(1ull << kFixShift);
+                            unsigned long long* ap = acc + (buf * kTilePix + (lp & 63)) * 3;
+                            fixed_add(ap + 0, __double2ull_rz(cr * fs));
+                            fixed_add(ap + 1, __double2ull_rz(cg * fs));
+                            fixed_add(ap + 2, __double2ull_rz(cb * fs));
+                            dest = 3;
+                        } else {
+                            bt[rec] = best.t;
+                            bk[rec] = best.k | (best.C == 0.0 ? (1 << 30) : 0);
+                            dest = 1;
+                        }
+                    }
+                    const unsigned mS = __ballot_sync(0xffffffffu, dest == 1), mF = __ballot_sync(0xffffffffu, dest == 3),
+                                   mB = __ballot_sync(0xffffffffu, dest == 3 && buf);
+                    if (dest == 1) qS[nS + __popc(mS & lt_mask)] = (uint8_t)rec;
+                    if (dest == 3) qF[nF + __popc(mF & lt_mask)] = (uint8_t)rec;
+                    nS += __popc(mS); nF += __popc(mF);
+                    infl1 -= __popc(mB); infl0 -= __popc(mF) - __popc(mB);
+                    if (dest) rec = -1;
+                }
             }
-            nS += m;
         }
     }
 

@@ -51,7 +51,7 @@ int main(int argc, char** argv) {
             rt::progressive_render pr(dw, cam, params, devices[0]);
             for (int k = 0; k < passes; ++k) {
                 const int upto = (int)((long long)sample_per_pixel * (k + 1) / passes);
-                if (upto > pr.samples_done()) pr.add(upto - pr.samples_done());
+                if (upto > pr.samples_done()) pr.add(upto - pr.samples_done(), /*want_stats=*/k == passes - 1);
                 std::cerr << "\rSamples done: " << pr.samples_done() << ' ' << std::flush;
             }
             img = pr.current();

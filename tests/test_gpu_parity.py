@@ -856,34 +856,40 @@ def test_accumulator_passes_equal_one_render(rt, book, mode):
     assert casts < st["casts"]
 
 
-def test_accumulator_64_passes_cost_one_render(rt, book):
-    """a 64-pass progressive render of the 1200x800 frame through the device-resident accumulator
-    against one render of the same samples (wall clock around both, GPU idle before each)."""
+@pytest.mark.parametrize("mode", [3, 0])
+def test_accumulator_64_passes_cost_one_render(rt, book, mode):
+    """a 64-pass progressive render of BASELINE config 3 (1200x800, 500 spp) through the device-resident
+    accumulator against one render of the same samples (wall clock around both, GPU idle before each).  Passes
+    alternate between two streams, so a pass's tail overlaps the next pass's start."""
     import time
     import torch
     from petershirleyraytracer_b200 import scenes
     c, r = book
-    W, H, spp, passes = 1200, 800, 256, 64
+    W, H, spp, passes = 1200, 800, 500, 64
     cam = scenes.book_camera(W, H)
     with rt.Scene(c, r) as sc, rt.Accumulator(W, H) as acc:
-        p = rt.make_params(W, H, spp, 50, seed=2, early_out=False, scan_mode=0)
-        rt.render_device(sc, cam, rt.make_params(W, H, 4, 50, seed=2, early_out=False, scan_mode=0), torch.empty(W * H * 4, dtype=torch.uint8, device="cuda").data_ptr())
+        kw = dict(seed=2, early_out=False, scan_mode=mode)
+        warm = torch.empty(W * H * 4, dtype=torch.uint8, device="cuda")
+        rt.render_device(sc, cam, rt.make_params(W, H, 4, 50, **kw), warm.data_ptr())
         rt.render_finish(sc)
+        acc.add(sc, cam, rt.make_params(W, H, 1, 50, **kw), want_stats=True)
+        acc.reset()
         frame = torch.empty(W * H * 4, dtype=torch.uint8, device="cuda")
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        rt.render_device(sc, cam, p, frame.data_ptr())
+        rt.render_device(sc, cam, rt.make_params(W, H, spp, 50, **kw), frame.data_ptr())
         rt.render_finish(sc)
         t_one = time.perf_counter() - t0
-        pp = rt.make_params(W, H, spp // passes, 50, seed=2, early_out=False, scan_mode=0)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(passes):
-            acc.add(sc, cam, pp)
+        for k in range(passes):
+            n = spp * (k + 1) // passes - spp * k // passes
+            acc.add(sc, cam, rt.make_params(W, H, n, 50, **kw))
         rgba = acc.frame()
         t_prog = time.perf_counter() - t0
+        assert acc.samples == spp
         assert np.array_equal(rgba, frame.cpu().numpy().reshape(H, W, 4))
-    _record_parity("progressive_64_passes_1200x800x256spp", {"single_render_s": t_one, "64_passes_s": t_prog, "ratio": t_prog / t_one})
+    _record_parity(f"progressive_64_passes_1200x800x500spp_mode{mode}", {"single_render_s": t_one, "64_passes_s": t_prog, "ratio": t_prog / t_one})
     assert t_prog < 1.05 * t_one + 0.01
 
 

@@ -1,0 +1,30 @@
+"""Linear cull-scan kernel (RT_SCAN_FILTERED, reference semantics): kernel-time Msamples/s and FP32-roofline fraction."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import petershirleyraytracer_b200 as rt
+from petershirleyraytracer_b200 import scenes
+
+def run(name, c, r, cam, W, H, spp, peak, **kw):
+    with rt.Scene(c, r) as sc:
+        p = rt.make_params(W, H, spp, 50, seed=1, scan_mode=0, **kw)
+        rt.render(sc, cam, p)
+        best = None
+        for _ in range(3):
+            _, _, st = rt.render(sc, cam, p)
+            if best is None or st["kernel_ms"] < best["kernel_ms"]:
+                best = st
+    st = best
+    tests = st["casts"] * len(r)
+    print(json.dumps(dict(name=name, kw=kw, spp=spp, ms=round(st["kernel_ms"], 2), msamples_s=round(st["samples"] / st["kernel_ms"] / 1e3, 1),
+                          frac=round(tests * 11 / (st["kernel_ms"] * 1e-3) / peak, 4), exact_per_cast=round(st["exact_tests"] / st["casts"], 3),
+                          overflows=st["overflows"])), flush=True)
+
+if __name__ == "__main__":
+    spp = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+    peak, _ = rt.measure_fp32_peak(0)
+    c, r = scenes.book_scene(11)
+    run("c3", c, r, scenes.book_camera(1200, 800), 1200, 800, spp, peak, early_out=False)
+    run("c3", c, r, scenes.book_camera(1200, 800), 1200, 800, spp, peak, early_out=True)
+    run("c3", c, r, scenes.book_camera(1200, 800), 1200, 800, spp, peak, early_out=False, tmin=0.001)
+    dc, dr = scenes.default_scene()
+    run("c1", dc, dr, rt.Camera.default(), 400, 225, 100, peak, early_out=False)
