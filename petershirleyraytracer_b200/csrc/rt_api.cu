@@ -184,8 +184,9 @@ int resolve_scan_mode(const rt_scene* sc, int mode, int* out) {
         return fail(RT_ERR_UNSUPPORTED, "scene has non-finite or huge (>1e15) coordinates: use RT_SCAN_EXACT");
     if (mode == RT_SCAN_BVH && !sc->d_bvh_nodes)
         return fail(RT_ERR_UNSUPPORTED, "no BVH for this scene (non-finite or huge coordinates): use RT_SCAN_EXACT");
-    if (mode == RT_SCAN_FILTERED && sc->npad > rt::kMaxLinear)
-        return fail(RT_ERR_UNSUPPORTED, "linear cull scan holds at most 4080 spheres (64 KB constant bank); use RT_SCAN_EXACT or the BVH");
+    if (mode == RT_SCAN_FILTERED && sc->npad > rt::kMaxLinearSmem)
+        return fail(RT_ERR_UNSUPPORTED, "linear cull scan holds at most 11520 spheres (4080 in the constant bank, beyond that one CTA's "
+                                        "shared memory); use RT_SCAN_EXACT or the BVH");
     *out = mode;
     return RT_OK;
 }
@@ -252,7 +253,8 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     if (mode == RT_SCAN_BVH) R = 1;  // traversal is divergent: one path per lane, more warps
     // cull array source: constant bank (default; FFMAs then read a uniform-register operand) or the
     // TMA-staged shared-memory copy (reserved[2] == 1), kept for A/B evidence
-    const bool use_const = p->reserved[2] != 1 && mode == RT_SCAN_FILTERED;
+    // (scenes beyond the 64 KB bank take the shared-memory variant: the only linear scan that can hold them)
+    const bool use_const = p->reserved[2] != 1 && mode == RT_SCAN_FILTERED && sc->npad <= rt::kMaxLinear;
     // One critical section from the wait on the previous constant-bank renders through this render's launch and
     // event record: a second host thread rendering another FILTERED scene on another stream of this device then
     // queues its copy into the bank strictly behind this kernel (and not between this copy and this launch).  Renders

@@ -22,6 +22,7 @@ constexpr int kCandCap = 12;        // survivors per cast kept in smem; more -> 
 constexpr int kScanStep = 12;       // cull entries per scan step; arrays are padded to a multiple of this ...
 constexpr int kScanPad = 8;         // ... plus this many never-pass entries (prefetch runs two groups ahead)
 constexpr int kMaxLinear = 4080;    // cull entries that fit the 64 KB constant bank (with the prefetch pad)
+constexpr int kMaxLinearSmem = 11520;  // ... that fit one CTA's shared memory next to its path state (TMA-staged variant)
 constexpr int kFixShift = 44;       // radiance accumulates as 20.44 fixed point (order-independent sums)
 constexpr int kNumStats = 10;
 
@@ -411,170 +412,149 @@ __device__ __forceinline__ bool exact_test_unordered(const double4* __restrict__
 constexpr int kBvhW = RT_BVH_WIDTH;  // children per device BVH node (== rt_bvh.h: kBvhWidth)
 static_assert(RT_BVH_WIDTH == 4 && RT_BVH_LEAF == 1, "the traversal is written for 4-wide nodes with single-sphere leaves (8-wide nodes and 2-6 sphere leaves were measured slower in round 1)");
 constexpr int kBvhStack = 48;
-// The traversal is split into a per-ray setup and a one-node step so that the wavefront kernel can hand a lane a new
-// ray the moment its traversal ends (rt_kernels.cuh: T phase); bvh_cast() runs the two for one ray to completion.
-struct BvhTrav {
-    float ivx, ivy, ivz;                  // 1/d per axis (0 for a static axis)
-    float clx, cly, clz, chx, chy, chz;   // -o/d, directed-rounded for the lo / hi planes
-    float bu;                             // pruning bound: an entry distance tn matters iff tn <= bu
-    int node, sp;
-    bool zx, zy, zz;                      // direction component exactly 0: static axis
-    int stack_n[kBvhStack];
-    float stack_t[kBvhStack];
-};
-
-// padded FP32 interval of the origin (covers its rounding): op = upper, om = lower end per axis
-__device__ __forceinline__ void bvh_origin_pad(double ox, double oy, double oz, float& opx, float& opy, float& opz,
-                                               float& omx, float& omy, float& omz) {
-    const float fx = (float)ox, fy = (float)oy, fz = (float)oz;
-    const float padx = fabsf(fx) * 2.384185791015625e-07f + 1e-37f, pady = fabsf(fy) * 2.384185791015625e-07f + 1e-37f,
-                padz = fabsf(fz) * 2.384185791015625e-07f + 1e-37f;  // 2^-22 |o|
-    opx = __fadd_ru(fx, padx); opy = __fadd_ru(fy, pady); opz = __fadd_ru(fz, padz);
-    omx = __fadd_rd(fx, -padx); omy = __fadd_rd(fy, -pady); omz = __fadd_rd(fz, -padz);
-}
-
-constexpr float kBvhUp = 1.0f + 1.9073486328125e-06f;     // 1 + 2^-19
-constexpr float kBvhInvDn = 1.0f + 3.814697265625e-06f;   // > 1 / (1 - 2^-19)
-
-// `bound`: distance of a hit already known (the start sphere's, see self_cast), else tmax.  Returns false if the ray
-// cannot be traversed (a direction component that is non-zero in FP64 but zero / denormal in FP32): sequential scan.
-__device__ __forceinline__ bool bvh_setup(BvhTrav& T, double ox, double oy, double oz, double dx, double dy, double dz,
-                                          double bound) {
-    float opx, opy, opz, omx, omy, omz;
-    bvh_origin_pad(ox, oy, oz, opx, opy, opz, omx, omy, omz);
-    // 1/d in FP32 (__frcp_rn of the rounded component): 2^-23 relative instead of the 2^-24 of rounding the FP64
-    // quotient -- the products below then carry 4 x 2^-24, inside the 1 +- 2^-19 slack -- and no FP64 division.
-    // A component that is exactly 0 makes the ray parallel to that slab pair: the axis then constrains no distance,
-    // it only decides (in bvh_step, per box) whether the origin's padded interval overlaps the slab at all.  With iv = 0
-    // and constants -inf / +inf both plane distances come out as -inf / +inf without any inf * 0.  (iv = inf would
-    // give fma(plane, inf, -+inf) = NaN for the plane on the far side of the origin, which fmaxf drops: a false
-    // miss.)  A non-zero component whose FP32 value is zero or denormal (|d| < 2^-126) is not static -- the ray does
-    // cross that slab at some huge t -- and no FP32 reciprocal can bound 1/d: such rays take the sequential scan.
-    T.zx = dx == 0.0; T.zy = dy == 0.0; T.zz = dz == 0.0;
-    const float kMinNormal = 1.17549435e-38f;
-    if ((!T.zx && fabsf((float)dx) < kMinNormal) || (!T.zy && fabsf((float)dy) < kMinNormal) ||
-        (!T.zz && fabsf((float)dz) < kMinNormal))
-        return false;
-    T.ivx = T.zx ? 0.f : __frcp_rn((float)dx); T.ivy = T.zy ? 0.f : __frcp_rn((float)dy); T.ivz = T.zz ? 0.f : __frcp_rn((float)dz);
-    // Slab distances as ONE FFMA per plane: (plane - o) * iv = fma(plane, iv, -(o * iv)).  The constant -(o*iv) is
-    // formed exactly in FP64 (24 x 24 bits) and rounded in the direction that keeps the plane's role conservative:
-    // for iv > 0 the lo planes give the near distance (must not be overestimated: round down) and the hi planes the
-    // far distance (round up); for iv < 0 the roles swap.  The FFMA's own rounding is relative to its result and is
-    // covered by the 1 +- 2^-19 factors.  (iv is never +-inf here: zero components are static axes, FP32-denormal
-    // ones left above.  iv = +-0 -- a component beyond the float range -- gives both planes the distance 0, which
-    // only asks that the origin lie inside the other two slabs: conservative.)
-    const double pxl = -((double)opx * (double)T.ivx), pyl = -((double)opy * (double)T.ivy), pzl = -((double)opz * (double)T.ivz);
-    const double pxh = -((double)omx * (double)T.ivx), pyh = -((double)omy * (double)T.ivy), pzh = -((double)omz * (double)T.ivz);
-    const float kFInf = __int_as_float(0x7f800000);
-    T.clx = T.zx ? -kFInf : (T.ivx > 0.f ? __double2float_rd(pxl) : __double2float_ru(pxl));
-    T.chx = T.zx ? kFInf : (T.ivx > 0.f ? __double2float_ru(pxh) : __double2float_rd(pxh));
-    T.cly = T.zy ? -kFInf : (T.ivy > 0.f ? __double2float_rd(pyl) : __double2float_ru(pyl));
-    T.chy = T.zy ? kFInf : (T.ivy > 0.f ? __double2float_ru(pyh) : __double2float_rd(pyh));
-    T.clz = T.zz ? -kFInf : (T.ivz > 0.f ? __double2float_rd(pzl) : __double2float_ru(pzl));
-    T.chz = T.zz ? kFInf : (T.ivz > 0.f ? __double2float_ru(pzh) : __double2float_rd(pzh));
-    // the pruning bound: entry distance tn may matter iff tn * (1 - 2^-19) <= RU(best t); kept pre-divided (rounded
-    // up, so the test only gets looser) so that a box costs one compare against it
-    T.bu = __fmul_ru(__double2float_ru(bound), kBvhInvDn);
-    T.node = 0; T.sp = 0;
-    return true;
-}
-
-// One wide node: four box tests, FP64 tests of the hit leaves, descend into the nearest hit inner child (the others go
-// to the stack) or pop.  Returns 0: T.node is the next node to visit; 1: traversal finished; 2: stack exhausted.
-__device__ __forceinline__ int bvh_step(const SceneDev& sc, BvhTrav& T, double ox, double oy, double oz, double dx,
-                                        double dy, double dz, const RcpA& dA, double tmin, double tmax, Best& best, int skip,
-                                        uint32_t& n_exact, uint32_t& n_nodes) {
-    // one wide node (32 bytes per child), structure of arrays: the same bound of four children per float4
-    constexpr int W = kBvhW;
-    const float4* nb = sc.bvh_nodes + 8 * T.node;
-    const float4 a0 = __ldg(nb + 0), a1 = __ldg(nb + 1), a2 = __ldg(nb + 2), a3 = __ldg(nb + 3), a4 = __ldg(nb + 4),
-                 a5 = __ldg(nb + 5), a6 = __ldg(nb + 6);
-    const float lx[W] = {a0.x, a0.y, a0.z, a0.w}, ly[W] = {a1.x, a1.y, a1.z, a1.w}, lz[W] = {a2.x, a2.y, a2.z, a2.w};
-    const float hx[W] = {a3.x, a3.y, a3.z, a3.w}, hy[W] = {a4.x, a4.y, a4.z, a4.w}, hz[W] = {a5.x, a5.y, a5.z, a5.w};
-    const int ch[W] = {__float_as_int(a6.x), __float_as_int(a6.y), __float_as_int(a6.z), __float_as_int(a6.w)};
-    ++n_nodes;
-    float tn[W];
-    bool hit[W];
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-        const float ax = fmaf(lx[i], T.ivx, T.clx), bx = fmaf(hx[i], T.ivx, T.chx);
-        const float ay = fmaf(ly[i], T.ivy, T.cly), by = fmaf(hy[i], T.ivy, T.chy);
-        const float az = fmaf(lz[i], T.ivz, T.clz), bz = fmaf(hz[i], T.ivz, T.chz);
-        tn[i] = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
-        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-        hit[i] = tn[i] <= tf * kBvhUp && tn[i] <= T.bu;   // (empty slots carry NaN boxes: tf = NaN, never hit)
-    }
-    if (T.zx || T.zy || T.zz) {  // static axes: the (padded) origin coordinate must lie inside the slab
-        float opx, opy, opz, omx, omy, omz;
-        bvh_origin_pad(ox, oy, oz, opx, opy, opz, omx, omy, omz);
-#pragma unroll
-        for (int i = 0; i < W; ++i) {
-            if (T.zx) hit[i] = hit[i] && lx[i] <= opx && hx[i] >= omx;
-            if (T.zy) hit[i] = hit[i] && ly[i] <= opy && hy[i] >= omy;
-            if (T.zz) hit[i] = hit[i] && lz[i] <= opz && hz[i] >= omz;
-        }
-    }
-    // hit leaves are resolved on the spot, one after the other in ONE rolled loop (each re-checked against the best
-    // found so far): a single copy of the FP64 test in the instruction stream -- with one copy per child slot the
-    // kernel outgrew the 32 KB instruction cache and stalled on instruction fetch
-    uint32_t leafm = 0u;
-#pragma unroll
-    for (int i = 0; i < W; ++i) leafm |= (hit[i] && ch[i] < 0) ? (1u << i) : 0u;
-#pragma unroll 1
-    while (leafm) {
-        const int i = __ffs((int)leafm) - 1;
-        leafm &= leafm - 1u;
-        const float tni = i == 0 ? tn[0] : (i == 1 ? tn[1] : (i == 2 ? tn[2] : tn[3]));
-        const int chi = i == 0 ? ch[0] : (i == 1 ? ch[1] : (i == 2 ? ch[2] : ch[3]));
-        const int k = (int)(((unsigned)chi & 0x7fffffffu) >> 3);   // single-sphere leaves carry the sphere index itself (rt_bvh.h)
-        if (tni <= T.bu && k != skip) {
-            ++n_exact;
-            if (exact_test_unordered(sc.exact, k, ox, oy, oz, dx, dy, dz, dA, tmin, tmax, best))
-                T.bu = __fmul_ru(__double2float_ru(best.t), kBvhInvDn);
-        }
-    }
-    // hit inner children: descend into the nearest, stack the others
-    int next = -1;
-    float next_t = 0.f;
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-        if (hit[i] && ch[i] >= 0 && tn[i] <= T.bu) {
-            int pn = ch[i];
-            float pt = tn[i];
-            if (next < 0 || pt < next_t) {   // new nearest: the old one (if any) goes to the stack
-                const int on = next; const float ot = next_t;
-                next = pn; next_t = pt;
-                pn = on; pt = ot;
-            }
-            if (pn >= 0) {
-                if (T.sp >= kBvhStack) return 2;
-                T.stack_n[T.sp] = pn; T.stack_t[T.sp] = pt; ++T.sp;
-            }
-        }
-    }
-    if (next >= 0) { T.node = next; return 0; }
-    while (T.sp > 0) {
-        --T.sp;
-        if (T.stack_t[T.sp] <= T.bu) { T.node = T.stack_n[T.sp]; return 0; }
-    }
-    return 1;
-}
-
 // `best` is in/out: a hit already known (the start sphere's, see self_cast) bounds the traversal from the first
 // node on; `skip` names a sphere that needs no further test (that start sphere; -1: none).
-// (An FP32 line test per leaf sphere before the FP64 test was measured in round 1: exact tests/cast 4.96 -> 1.21, but
-//  6 % slower overall -- the per-cast cull constants cost more than the FP64 tests they save.)
 __device__ __forceinline__ void bvh_cast(const SceneDev& sc, double ox, double oy, double oz, double dx, double dy,
                                          double dz, double A, double tmin, double tmax, Best& best, int skip,
                                          uint32_t& n_exact, uint32_t& n_nodes, bool& overflow) {
     const RcpA dA = make_rcp(A);
-    BvhTrav T;
-    if (!bvh_setup(T, ox, oy, oz, dx, dy, dz, best.k >= 0 ? best.t : tmax)) { overflow = true; return; }
-    int state;
-    do {
-        state = bvh_step(sc, T, ox, oy, oz, dx, dy, dz, dA, tmin, tmax, best, skip, n_exact, n_nodes);
-    } while (state == 0);
-    overflow = state == 2;
+    // (An FP32 line test per leaf sphere before the FP64 test was measured: exact tests/cast 4.96 -> 1.21,
+    //  but 6 % slower overall -- the per-cast cull constants cost more than the FP64 tests they save.)
+    const float kUp = 1.0f + 1.9073486328125e-06f;  // 1 + 2^-19
+    const float fx = (float)ox, fy = (float)oy, fz = (float)oz;
+    const float padx = fabsf(fx) * 2.384185791015625e-07f + 1e-37f, pady = fabsf(fy) * 2.384185791015625e-07f + 1e-37f,
+                padz = fabsf(fz) * 2.384185791015625e-07f + 1e-37f;  // 2^-22 |o|: covers the FP32 rounding of o
+    const float opx = __fadd_ru(fx, padx), opy = __fadd_ru(fy, pady), opz = __fadd_ru(fz, padz);
+    const float omx = __fadd_rd(fx, -padx), omy = __fadd_rd(fy, -pady), omz = __fadd_rd(fz, -padz);
+    // 1/d in FP32 (__frcp_rn of the rounded component): 2^-23 relative instead of the 2^-24 of rounding the FP64
+    // quotient -- the products below then carry 4 x 2^-24, inside the 1 +- 2^-19 slack -- and no FP64 division
+    // A component that is exactly 0 makes the ray parallel to that slab pair: the axis then constrains no distance,
+    // it only decides (below, per box) whether the origin's padded interval overlaps the slab at all.  With iv = 0
+    // and constants -inf / +inf both plane distances come out as -inf / +inf without any inf * 0.  (iv = inf would
+    // give fma(plane, inf, -+inf) = NaN for the plane on the far side of the origin, which fmaxf drops: a false
+    // miss.)  A non-zero component whose FP32 value is zero or denormal (|d| < 2^-126) is not static -- the ray does
+    // cross that slab at some huge t -- and no FP32 reciprocal can bound 1/d: such rays take the sequential scan.
+    const bool zx = dx == 0.0, zy = dy == 0.0, zz = dz == 0.0;
+    const bool zany = zx || zy || zz;
+    {
+        const float kMinNormal = 1.17549435e-38f;
+        if ((!zx && fabsf((float)dx) < kMinNormal) || (!zy && fabsf((float)dy) < kMinNormal) ||
+            (!zz && fabsf((float)dz) < kMinNormal)) {
+            overflow = true;
+            return;
+        }
+    }
+    const float ivx = zx ? 0.f : __frcp_rn((float)dx), ivy = zy ? 0.f : __frcp_rn((float)dy),
+                ivz = zz ? 0.f : __frcp_rn((float)dz);
+    // Slab distances as ONE FFMA per plane: (plane - o) * iv = fma(plane, iv, -(o * iv)).  The constant -(o*iv) is
+    // formed exactly in FP64 (24 x 24 bits) and rounded in the direction that keeps the plane's role conservative:
+    // for iv > 0 the lo planes give the near distance (must not be overestimated: round down) and the hi planes the
+    // far distance (round up); for iv < 0 the roles swap.  The FFMA's own rounding is relative to its result and is
+    // covered by the 1 +- 2^-19 factors like before.  (iv is never +-inf here: zero components are static axes,
+    // FP32-denormal ones left above.  iv = +-0 -- a component beyond the float range -- gives both planes the
+    // distance 0, which only asks that the origin lie inside the other two slabs: conservative.)
+    const double pxl = -((double)opx * (double)ivx), pyl = -((double)opy * (double)ivy), pzl = -((double)opz * (double)ivz);
+    const double pxh = -((double)omx * (double)ivx), pyh = -((double)omy * (double)ivy), pzh = -((double)omz * (double)ivz);
+    const float kFInf = __int_as_float(0x7f800000);
+    const float clx = zx ? -kFInf : (ivx > 0.f ? __double2float_rd(pxl) : __double2float_ru(pxl)), chx = zx ? kFInf : (ivx > 0.f ? __double2float_ru(pxh) : __double2float_rd(pxh));
+    const float cly = zy ? -kFInf : (ivy > 0.f ? __double2float_rd(pyl) : __double2float_ru(pyl)), chy = zy ? kFInf : (ivy > 0.f ? __double2float_ru(pyh) : __double2float_rd(pyh));
+    const float clz = zz ? -kFInf : (ivz > 0.f ? __double2float_rd(pzl) : __double2float_ru(pzl)), chz = zz ? kFInf : (ivz > 0.f ? __double2float_ru(pzh) : __double2float_rd(pzh));
+    // the pruning bound: entry distance tn may matter iff tn * (1 - 2^-19) <= RU(best t); kept pre-divided (rounded
+    // up, so the test only gets looser) so that a box costs one compare against it
+    const float kInvDn = 1.0f + 3.814697265625e-06f;  // > 1 / (1 - 2^-19)
+    float bu = __fmul_ru(__double2float_ru(best.k >= 0 ? best.t : tmax), kInvDn);
+    int stack_n[kBvhStack];
+    float stack_t[kBvhStack];
+    int sp = 0, node = 0;
+    for (;;) {
+        // one wide node (32 bytes per child), structure of arrays: the same bound of four children per float4
+        constexpr int W = kBvhW, Q = kBvhW / 4;
+        const float4* nb = sc.bvh_nodes + 8 * Q * node;
+        float lx[W], ly[W], lz[W], hx[W], hy[W], hz[W];
+        int ch[W];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const float4 a0 = __ldg(nb + 0 * Q + q), a1 = __ldg(nb + 1 * Q + q), a2 = __ldg(nb + 2 * Q + q);
+            const float4 a3 = __ldg(nb + 3 * Q + q), a4 = __ldg(nb + 4 * Q + q), a5 = __ldg(nb + 5 * Q + q);
+            const float4 a6 = __ldg(nb + 6 * Q + q);
+            lx[4 * q] = a0.x; lx[4 * q + 1] = a0.y; lx[4 * q + 2] = a0.z; lx[4 * q + 3] = a0.w;
+            ly[4 * q] = a1.x; ly[4 * q + 1] = a1.y; ly[4 * q + 2] = a1.z; ly[4 * q + 3] = a1.w;
+            lz[4 * q] = a2.x; lz[4 * q + 1] = a2.y; lz[4 * q + 2] = a2.z; lz[4 * q + 3] = a2.w;
+            hx[4 * q] = a3.x; hx[4 * q + 1] = a3.y; hx[4 * q + 2] = a3.z; hx[4 * q + 3] = a3.w;
+            hy[4 * q] = a4.x; hy[4 * q + 1] = a4.y; hy[4 * q + 2] = a4.z; hy[4 * q + 3] = a4.w;
+            hz[4 * q] = a5.x; hz[4 * q + 1] = a5.y; hz[4 * q + 2] = a5.z; hz[4 * q + 3] = a5.w;
+            ch[4 * q] = __float_as_int(a6.x); ch[4 * q + 1] = __float_as_int(a6.y);
+            ch[4 * q + 2] = __float_as_int(a6.z); ch[4 * q + 3] = __float_as_int(a6.w);
+        }
+        ++n_nodes;
+        float tn[W];
+        bool hit[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            const float ax = fmaf(lx[i], ivx, clx), bx = fmaf(hx[i], ivx, chx);
+            const float ay = fmaf(ly[i], ivy, cly), by = fmaf(hy[i], ivy, chy);
+            const float az = fmaf(lz[i], ivz, clz), bz = fmaf(hz[i], ivz, chz);
+            tn[i] = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+            const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+            hit[i] = tn[i] <= tf * kUp && tn[i] <= bu;   // (empty slots carry NaN boxes: tf = NaN, never hit)
+        }
+        if (zany) {  // static axes: the (padded) origin coordinate must lie inside the slab
+#pragma unroll
+            for (int i = 0; i < W; ++i) {
+                if (zx) hit[i] = hit[i] && lx[i] <= opx && hx[i] >= omx;
+                if (zy) hit[i] = hit[i] && ly[i] <= opy && hy[i] >= omy;
+                if (zz) hit[i] = hit[i] && lz[i] <= opz && hz[i] >= omz;
+            }
+        }
+        // hit leaves are resolved on the spot, one after the other in ONE rolled loop (each re-checked against the best
+        // found so far): a single copy of the FP64 test in the instruction stream -- with one copy per child slot the
+        // kernel outgrew the 32 KB instruction cache and stalled on instruction fetch
+        uint32_t leafm = 0u;
+#pragma unroll
+        for (int i = 0; i < W; ++i) leafm |= (hit[i] && ch[i] < 0) ? (1u << i) : 0u;
+#pragma unroll 1
+        while (leafm) {
+            const int i = __ffs((int)leafm) - 1;
+            leafm &= leafm - 1u;
+            const float tni = i == 0 ? tn[0] : (i == 1 ? tn[1] : (i == 2 ? tn[2] : tn[3]));
+            const int chi = i == 0 ? ch[0] : (i == 1 ? ch[1] : (i == 2 ? ch[2] : ch[3]));
+            const int k = (int)(((unsigned)chi & 0x7fffffffu) >> 3);   // single-sphere leaves carry the sphere index itself (rt_bvh.h)
+            if (tni <= bu && k != skip) {
+                ++n_exact;
+                if (exact_test_unordered(sc.exact, k, ox, oy, oz, dx, dy, dz, dA, tmin, tmax, best))
+                    bu = __fmul_ru(__double2float_ru(best.t), kInvDn);
+            }
+        }
+        // hit inner children: descend into the nearest, stack the others
+        int next = -1;
+        float next_t = 0.f;
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            if (hit[i] && ch[i] >= 0 && tn[i] <= bu) {
+                int pn = ch[i];
+                float pt = tn[i];
+                if (next < 0 || pt < next_t) {   // new nearest: the old one (if any) goes to the stack
+                    const int on = next; const float ot = next_t;
+                    next = pn; next_t = pt;
+                    pn = on; pt = ot;
+                }
+                if (pn >= 0) {
+                    if (sp >= kBvhStack) { overflow = true; return; }
+                    stack_n[sp] = pn; stack_t[sp] = pt; ++sp;
+                }
+            }
+        }
+        if (next >= 0) {
+            node = next;
+        } else {
+            bool found = false;
+            while (sp > 0) {
+                --sp;
+                if (stack_t[sp] <= bu) { node = stack_n[sp]; found = true; break; }
+            }
+            if (!found) break;
+        }
+    }
 }
 
 // ---------------------------------------------------------------- start-sphere test + tie grid (rt_bvh.h: TieGridHost)
@@ -594,12 +574,6 @@ __device__ __forceinline__ bool tie_candidate(const float4 s, float fx, float fy
     const float w = fmaf(s.x, s.x, fmaf(s.y, s.y, fmaf(s.z, s.z, s.w * s.w)));
     const float tol = fmaf(1.9073486328125e-06f, o2 + w, rho * fmaf(2.0002f, s.w, rho));
     return !(fabsf(q) > tol);   // (NaN counts as a candidate)
-}
-
-// reach of a kept hit at distance t along a ray with dot(dir, dir) = A, in FP32, rounded up: a sphere can only yield an
-// accepted root <= t if its surface comes within t * |dir| of the origin (see tie_candidate).  +inf while nothing is kept.
-__device__ __forceinline__ float hit_reach(double t, double A) {
-    return __fmul_ru(__fmul_ru(__double2float_ru(t), __fsqrt_ru(__double2float_ru(A))), 1.0000019f);
 }
 
 // The part of a BVH-mode cast that needs no traversal: FP64 sphere::hit of the start sphere, then the tie grid.
@@ -633,7 +607,7 @@ __device__ __forceinline__ bool self_cast(const SceneDev& sc, int self, double o
         if (e == 0) {
             if (!(sc.tie_ok && best.k == self && dA.fast)) break;
             if (best.t != 0.0) {   // reach = t * |dir|, rounded up
-                rho = hit_reach(best.t, A);
+                rho = __fmul_ru(__fmul_ru(__double2float_ru(best.t), __fsqrt_ru(__double2float_ru(A))), 1.0000019f);
                 if (!(rho <= sc.tie_rho_max)) break;   // (also NaN / negative t)
             }
             fx = (float)ox; fy = (float)oy; fz = (float)oz;

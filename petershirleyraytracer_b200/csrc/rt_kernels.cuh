@@ -138,7 +138,7 @@ __device__ __forceinline__ void flush_unit(const RenderArgs& a, const Unit& u, u
     for (int j = 0; j < kTilePix * 3 / 32; ++j) accp[j * 32 + lane] = 0ull;
 }
 
-template <int R>
+template <int R, int kSrc>
 struct RenderTraits {
 #ifndef RT_MINB1
 #define RT_MINB1 5
@@ -149,13 +149,15 @@ struct RenderTraits {
 #ifndef RT_MINB4
 #define RT_MINB4 3
 #endif
-    static constexpr int kMinBlocks = R >= 4 ? RT_MINB4 : (R == 2 ? RT_MINB2 : RT_MINB1);  // CTAs of 128 threads per SM (register budget)
+    // CTAs of 128 threads per SM (register budget).  The shared-memory variant (kSrc == 0) reads its cull entries with
+    // LDS.128 into vector registers: at 96 registers it spilled 40-68 bytes, so it gets 128 (4 CTAs/SM).
+    static constexpr int kMinBlocks = R >= 4 ? RT_MINB4 : (kSrc == 0 ? 4 : (R == 2 ? RT_MINB2 : RT_MINB1));
 };
 
 // kSrc: where the cast looks for hits: 0 = cull array in TMA-staged shared memory, 1 = cull array in the
 // constant bank (default), 2 = flattened BVH (large scenes)
 template <int R, int kSrc>
-__global__ void __launch_bounds__(kThreads, RenderTraits<R>::kMinBlocks) render_kernel(const __grid_constant__ RenderArgs a) {
+__global__ void __launch_bounds__(kThreads, RenderTraits<R, kSrc>::kMinBlocks) render_kernel(const __grid_constant__ RenderArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t s_mbar;
     constexpr bool kConst = kSrc == 1, kBvh = kSrc == 2;
@@ -393,10 +395,6 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R>::kMinBlocks) render_
 #define RT_WAVE_REGEN 24
 #endif
 constexpr int kPool = RT_WAVE_POOL;        // path records per warp
-#ifndef RT_WAVE_FETCH
-#define RT_WAVE_FETCH 8
-#endif
-constexpr int kFetchMin = RT_WAVE_FETCH;   // T phase: idle lanes take new rays in batches of at least this many
 constexpr int kRegenMin = RT_WAVE_REGEN;   // free records are refilled in batches of at least this many (a regeneration
                                            // round costs the same for 2 lanes as for 32), so (kPool - kRegenMin) / 2 >= 32
                                            // keeps both phases at full width
@@ -561,18 +559,26 @@ __global__ void __launch_bounds__(kThreads, RT_WAVE_MINB) render_wave_kernel(con
                 const int depth = (int)(mt.w & 0xffffu), lp = (int)(mt.w >> 16);  // lp: bits 0-5 pixel in tile, bit 6 buffer
                 buf = lp >> 6;
                 const int bounces = a.max_depth - depth;
-                const int kk = bk[rec];   // (a hit: misses end in the T phase)
+                const double A = ddot(dx, dy, dz, dx, dy, dz);  // programs/sphere.cc:9
+                const int kk = bk[rec];
                 ++n_casts;
-                {
+                if (kk < 0) {
+                    // miss: sky (programs/main.cc:46-48) * attenuation -> fixed-point accumulate
+                    double cr, cg, cb;
+                    sky_color(a.sh, dy, A, bounces, cr, cg, cb);
+                    const double fs = (double)(1ull << kFixShift);
+                    unsigned long long* ap = acc + (buf * kTilePix + (lp & 63)) * 3;
+                    fixed_add(ap + 0, __double2ull_rz(cr * fs));
+                    fixed_add(ap + 1, __double2ull_rz(cg * fs));
+                    fixed_add(ap + 2, __double2ull_rz(cb * fs));
+                    dest = 3;
+                } else {
                     Best hitb;
                     hitb.t = bt[rec]; hitb.k = kk & 0x3fffffff; hitb.C = (kk >> 30) & 1 ? 0.0 : 1.0;
                     if (bounces == 0) ++n_primary;
                     if (a.early_out && hitb.t == 0.0 && hitb.C == 0.0) {
                         // origin stays on this sphere with C == 0: every later cast hits at t == 0 -> black
                         ++n_early; ++n_black;
-                        dest = 3;
-                    } else if (depth == 0) {  // programs/main.cc:36-37: the next ray_color call has depth < 0 -> black
-                        ++n_black;
                         dest = 3;
                     } else {
                         const Record rc = make_record(a.sc, hitb, ox, oy, oz, dx, dy, dz);
@@ -582,7 +588,10 @@ __global__ void __launch_bounds__(kThreads, RT_WAVE_MINB) render_wave_kernel(con
                         const double ndx = dsub(dadd(dadd(rc.px, rc.nx), rx), rc.px);
                         const double ndy = dsub(dadd(dadd(rc.py, rc.ny), ry), rc.py);
                         const double ndz = dsub(dadd(dadd(rc.pz, rc.nz), rz), rc.pz);
-                        {
+                        if (depth == 0) {  // programs/main.cc:36-37: the next ray_color call has depth < 0
+                            ++n_black;
+                            dest = 3;
+                        } else {
                             st[0 * kPool + rec] = rc.px; st[1 * kPool + rec] = rc.py; st[2 * kPool + rec] = rc.pz;
                             st[3 * kPool + rec] = ndx; st[4 * kPool + rec] = ndy; st[5 * kPool + rec] = ndz;
                             mt.w = (uint32_t)(depth - 1) | ((uint32_t)lp << 16);
@@ -612,80 +621,37 @@ __global__ void __launch_bounds__(kThreads, RT_WAVE_MINB) render_wave_kernel(con
             nS += __popc(mS); nT += __popc(mT); nF += __popc(mF);
             infl1 -= __popc(mB); infl0 -= __popc(mF) - __popc(mB);
         } else {
-            // ================= T: BVH traversal bounded by the start sphere's hit
-            // Lanes take records from the T queue, traverse one wide node per iteration, and a lane whose ray is done
-            // hands in its result (hit -> S queue; miss -> sky colour, record freed) and takes the next record while
-            // the others keep going: the traversal loop stays full although rays visit 1 to 15 nodes.  (Fetching is
-            // batched -- kFetchMin idle lanes -- because the per-ray setup is ~100 instructions.)
-            int rec = -1, skip = -1, state = 0;
-            double ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1;
-            Best best;
-            best.t = kInf; best.C = 1.0; best.k = -1;
-            RcpA dA = make_rcp(1.0);
-            BvhTrav T;
-            T.node = 0; T.sp = 0;
-            for (;;) {
-                const unsigned idle = __ballot_sync(0xffffffffu, rec < 0);
-                if (nT > 0 && __popc(idle) >= kFetchMin) {
-                    const int rank = __popc(idle & lt_mask);
-                    if (rec < 0 && rank < nT) {
-                        rec = (int)qT[nT - 1 - rank];
-                        ox = st[0 * kPool + rec]; oy = st[1 * kPool + rec]; oz = st[2 * kPool + rec];
-                        dx = st[3 * kPool + rec]; dy = st[4 * kPool + rec]; dz = st[5 * kPool + rec];
-                        const double A = ddot(dx, dy, dz, dx, dy, dz);
-                        const int kk = bk[rec];
-                        best.t = bt[rec]; best.k = kk < 0 ? -1 : (kk & 0x3fffffff); best.C = (kk >= 0 && ((kk >> 30) & 1)) ? 0.0 : 1.0;
-                        skip = selfk[rec];
-                        dA = make_rcp(A);
-                        const bool sane = A > 0.0 && A < kInf && (ox * ox + oy * oy + oz * oz) < kCullMaxMag2;
-                        state = 0;
-                        if (!(sane && a.tmin >= 0.0) || !bvh_setup(T, ox, oy, oz, dx, dy, dz, best.k >= 0 ? best.t : kInf)) state = 2;
-                    }
-                    nT -= min(__popc(idle), nT);
+            // ================= T: BVH traversal bounded by the start sphere's hit, every lane to completion.
+            // (Measured and rejected, profiles/r2_ab_fetch.txt / r2_ab_wave.txt: handing finished lanes the next record
+            //  inside the traversal loop, one node per iteration, at batch sizes 4..32: 5-25 % slower; shading missed rays
+            //  here instead of in S: -1..-9 %; drawing a bounce's random point one bounce ahead: -2..-9 %.)
+            const int m = min(nT, 32);
+            const bool active = lane < m;
+            const int rec = active ? (int)qT[nT - m + lane] : 0;
+            nT -= m;
+            if (active) {
+                const double ox = st[0 * kPool + rec], oy = st[1 * kPool + rec], oz = st[2 * kPool + rec];
+                const double dx = st[3 * kPool + rec], dy = st[4 * kPool + rec], dz = st[5 * kPool + rec];
+                const double A = ddot(dx, dy, dz, dx, dy, dz);
+                const int kk = bk[rec];
+                Best best;
+                best.t = bt[rec]; best.k = kk < 0 ? -1 : (kk & 0x3fffffff); best.C = (kk >= 0 && ((kk >> 30) & 1)) ? 0.0 : 1.0;
+                const bool sane = A > 0.0 && A < kInf && (ox * ox + oy * oy + oz * oz) < kCullMaxMag2;
+                bool seq = !(sane && a.tmin >= 0.0);   // such rays take the sequential FP64 scan
+                if (!seq) {
+                    bool deep = false;
+                    bvh_cast(a.sc, ox, oy, oz, dx, dy, dz, A, a.tmin, kInf, best, selfk[rec], n_exact, n_nodes, deep);
+                    seq = deep;   // traversal stack exhausted (degenerate tree) / FP32-denormal direction component
                 }
-                if (__ballot_sync(0xffffffffu, rec >= 0) == 0u) break;
-                if (rec >= 0 && state == 0)
-                    state = bvh_step(a.sc, T, ox, oy, oz, dx, dy, dz, dA, a.tmin, kInf, best, skip, n_exact, n_nodes);
-                if (rec >= 0 && state == 2) {   // not traversable / stack exhausted: the sequential FP64 scan (rare)
+                if (seq) {
                     ++n_ovf;
-                    full_scan_cold(a.sc, ox, oy, oz, dx, dy, dz, dA.A, a.tmin, &best, &n_exact);
-                    state = 1;
+                    full_scan_cold(a.sc, ox, oy, oz, dx, dy, dz, A, a.tmin, &best, &n_exact);
                 }
-                const unsigned fin = __ballot_sync(0xffffffffu, rec >= 0 && state == 1);
-                if (fin) {
-                    int dest = 0, buf = 0;
-                    if (rec >= 0 && state == 1) {
-                        if (best.k < 0) {
-                            // miss: the path ends here with the sky colour (programs/main.cc:46-48) times its attenuation
-                            // -> fixed-point accumulate.  (In this phase a third of the finishing lanes miss; in S one
-                            // record in 24 would.)
-                            const uint4 mt = meta[rec];
-                            const int depth = (int)(mt.w & 0xffffu), lp = (int)(mt.w >> 16);
-                            buf = lp >> 6;
-                            ++n_casts;
-                            double cr, cg, cb;
-                            sky_color(a.sh, dy, dA.A, a.max_depth - depth, cr, cg, cb);
-                            const double fs = (double)(1ull << kFixShift);
-                            unsigned long long* ap = acc + (buf * kTilePix + (lp & 63)) * 3;
-                            fixed_add(ap + 0, __double2ull_rz(cr * fs));
-                            fixed_add(ap + 1, __double2ull_rz(cg * fs));
-                            fixed_add(ap + 2, __double2ull_rz(cb * fs));
-                            dest = 3;
-                        } else {
-                            bt[rec] = best.t;
-                            bk[rec] = best.k | (best.C == 0.0 ? (1 << 30) : 0);
-                            dest = 1;
-                        }
-                    }
-                    const unsigned mS = __ballot_sync(0xffffffffu, dest == 1), mF = __ballot_sync(0xffffffffu, dest == 3),
-                                   mB = __ballot_sync(0xffffffffu, dest == 3 && buf);
-                    if (dest == 1) qS[nS + __popc(mS & lt_mask)] = (uint8_t)rec;
-                    if (dest == 3) qF[nF + __popc(mF & lt_mask)] = (uint8_t)rec;
-                    nS += __popc(mS); nF += __popc(mF);
-                    infl1 -= __popc(mB); infl0 -= __popc(mF) - __popc(mB);
-                    if (dest) rec = -1;
-                }
+                bt[rec] = best.t;
+                bk[rec] = best.k < 0 ? -1 : (best.k | (best.C == 0.0 ? (1 << 30) : 0));
+                qS[nS + lane] = (uint8_t)rec;
             }
+            nS += m;
         }
     }
 

@@ -24,6 +24,10 @@ if __name__ == "__main__":
     peak, _ = rt.measure_fp32_peak(0)
     c, r = scenes.book_scene(11)
     run("c3", c, r, scenes.book_camera(1200, 800), 1200, 800, spp, peak, early_out=False)
+    try:
+        run("c3", c, r, scenes.book_camera(1200, 800), 1200, 800, spp, peak, early_out=False, paths_per_lane=3)
+    except Exception as e:  # noqa: BLE001  (libraries built before R = 3 existed)
+        print("R=3:", e)
     run("c3", c, r, scenes.book_camera(1200, 800), 1200, 800, spp, peak, early_out=True)
     run("c3", c, r, scenes.book_camera(1200, 800), 1200, 800, spp, peak, early_out=False, tmin=0.001)
     dc, dr = scenes.default_scene()
