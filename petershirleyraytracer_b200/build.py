@@ -38,15 +38,30 @@ def _newer(target: str, sources: list[str]) -> bool:
     return all(os.path.getmtime(s) <= t for s in sources if os.path.exists(s))
 
 
+def _digest(sources: list[str], flags: list[str]) -> str:
+    """Content hash of the sources and the compiler flags: the library is rebuilt when THIS changes (not when a
+    timestamp does -- a checkout or a copied tree can carry a stale .so that is newer than every source)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(flags).encode())
+    for s in sorted(sources):
+        h.update(os.path.basename(s).encode())
+        with open(s, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
     src_dir = os.path.join(PKG_DIR, "csrc")
     sources = [os.path.join(src_dir, f) for f in sorted(os.listdir(src_dir))] + [os.path.join(REPO, "include", "rt.h")]
-    if not force and _newer(LIB_PATH, sources):
+    stamp, digest = LIB_PATH + ".sha256", _digest(sources, NVCC_FLAGS)
+    if not force and not verbose and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB_PATH
     cmd = [_nvcc(), *NVCC_FLAGS, "-shared", os.path.join(src_dir, "rt_api.cu"), "-o", LIB_PATH]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True, cwd=PKG_DIR)
+    with open(stamp, "w") as f:
+        f.write(digest + "\n")
     return LIB_PATH
 
 

@@ -174,12 +174,12 @@ void tile_layout(const rt_params* p, rt_tile_layout* L) {
     L->shard_bytes = (int64_t)L->tiles_per_shard * rt::kTilePix * 4;
 }
 
-// AUTO: the BVH traversal wherever a BVH was built.  With the 4-wide SAH build it is faster than the linear cull
-// scan from 40 spheres up on B200 (tools/mode_compare.py, profiles/r1_mode_compare.txt: 40: 695 vs 631 Msamples/s,
-// 145: 576 vs 419, 485: 466 vs 208, 1939: 442 vs 45); for a handful of spheres the two tie (2: 1033 vs 1013) and the
-// scan's single step needs no tree, so the scan is kept below 16.
+// AUTO: the BVH mode (wavefront kernel: start-sphere test + tie grid, traversal for the rest) wherever a tree was built.
+// Round 1 kept the linear cull scan below 16 spheres (the two tied there); with the round-2 kernel the BVH mode wins
+// from the reference's own two-sphere scene up (1084 vs 1036 Msamples/s, profiles/r2_ab_wave.txt) and by 3.6x at 485
+// spheres (778 vs 215), so AUTO takes it for every scene of two or more spheres.
 int resolve_scan_mode(const rt_scene* sc, int mode, int* out) {
-    if (mode == RT_SCAN_AUTO) mode = (!sc->cull_ok) ? RT_SCAN_EXACT : (sc->n < 16 ? RT_SCAN_FILTERED : RT_SCAN_BVH);
+    if (mode == RT_SCAN_AUTO) mode = (!sc->cull_ok) ? RT_SCAN_EXACT : (sc->n < 2 ? RT_SCAN_FILTERED : RT_SCAN_BVH);
     if (mode == RT_SCAN_FILTERED && !sc->cull_ok)
         return fail(RT_ERR_UNSUPPORTED, "scene has non-finite or huge (>1e15) coordinates: use RT_SCAN_EXACT");
     if (mode == RT_SCAN_BVH && !sc->d_bvh_nodes)
