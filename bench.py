@@ -256,6 +256,7 @@ class GpuBench:
         torch.cuda.synchronize()
         if self.world > 1:
             dist.barrier()
+        local_kernel_ms = kern_ms
         t = torch.tensor([tot_ms, kern_ms], dtype=torch.float64, device=self.dev)
         cnt = torch.tensor([stats["sphere_tests"], stats["node_tests"], stats["exact_tests"], stats["casts"], stats["samples"],
                             stats["self_resolved"]], dtype=torch.float64, device=self.dev)
@@ -263,7 +264,7 @@ class GpuBench:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(cnt)
         keys = ("sphere_tests", "node_tests", "exact_tests", "casts", "samples", "self_resolved")
-        return {"ms": t[0].item(), "kernel_ms": t[1].item(), "launches": launches, "steps": nsteps,
+        return {"ms": t[0].item(), "kernel_ms": t[1].item(), "kernel_ms_this_rank": local_kernel_ms, "launches": launches, "steps": nsteps,
                 "value": self.samples_per_step * nsteps / (t[0].item() * 1e-3) / 1e6,
                 "counts": dict(zip(keys, (x.item() for x in cnt)))}     # whole-job sums of the last step
 

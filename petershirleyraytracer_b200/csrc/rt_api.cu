@@ -277,22 +277,30 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
         }
     }
     rt::RenderSmem S = rt::render_smem(use_const ? 0 : a.sc.npad, R);
+    int threads = rt::kThreads;
     void (*kern)(const rt::RenderArgs) = nullptr;
     if (mode == RT_SCAN_BVH && p->reserved[2] == 2) kern = rt::render_kernel<1, 2>;   // round-1 traversal kernel (A/B evidence only)
-    else if (mode == RT_SCAN_BVH) { kern = rt::render_wave_kernel; S.total = rt::wave_smem().total; }
+    else if (mode == RT_SCAN_BVH) { kern = rt::render_wave_kernel; S.total = rt::wave_smem().total; threads = rt::kWaveThreads; }
     else if (use_const) kern = R == 1 ? rt::render_kernel<1, 1> : (R == 2 ? rt::render_kernel<2, 1> : rt::render_kernel<4, 1>);
     else kern = R == 1 ? rt::render_kernel<1, 0> : (R == 2 ? rt::render_kernel<2, 0> : rt::render_kernel<4, 0>);
     RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
     int per_sm = 0;
-    RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, rt::kThreads, S.total));
+    RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, S.total));
     if (per_sm < 1) return fail(RT_ERR_CUDA, "render kernel does not fit on an SM");
     const int full_grid = sc->sm_count * per_sm;  // persistent: every resident warp pulls work units
 
-    // Work units = (tile, sample chunk).  Enough chunks that every resident warp sees ~64 units (the queue
-    // then balances to ~1%), but at least 8 samples per pixel and chunk; reserved[1] overrides (tests).
-    const int warps = full_grid * rt::kWarps;
-    int chunks = (64 * warps + a.tiles_local - 1) / (a.tiles_local > 0 ? a.tiles_local : 1);
-    const int max_chunks = (p->spp + 7) / 8;
+    // Work units = (tile, sample chunk).  A launch ends with about one unit's duration of ramp-down, so units should be
+    // short -- but a warp holds only two units at a time, and a unit whose last paths are still bouncing blocks the
+    // hand-out of the next one.  Measured on an eighth of the C3 frame (tools/chunk_probe.py, profiles/r2_chunk_probe.txt):
+    // the linear-scan kernel (64 paths per warp) is best at 4 samples per pixel and unit (0.995 of the full-frame rate;
+    // 8: 0.990, 2: 0.977), the wavefront kernel (96 records per warp) at 16 (0.956; 8: 0.946, 4: 0.89).  reserved[1]
+    // overrides (tests).
+    const int warps_per_cta = threads / 32;
+    const int warps = full_grid * warps_per_cta;
+    const bool wave = mode == RT_SCAN_BVH && p->reserved[2] != 2;
+    const int min_chunk_spp = wave ? 16 : 4, units_per_warp = wave ? 64 : 256;
+    int chunks = (units_per_warp * warps + a.tiles_local - 1) / (a.tiles_local > 0 ? a.tiles_local : 1);
+    const int max_chunks = (p->spp + min_chunk_spp - 1) / min_chunk_spp;
     if (chunks > max_chunks) chunks = max_chunks;
     if (p->reserved[1] > 0) chunks = p->reserved[1] < p->spp ? p->reserved[1] : p->spp;
     if (chunks < 1) chunks = 1;
@@ -300,7 +308,7 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     a.chunks = (p->spp + a.chunk_spp - 1) / a.chunk_spp;  // no empty chunk
     a.units_local = a.tiles_local * a.chunks;
     int grid = full_grid;
-    const int need = (a.units_local + rt::kWarps - 1) / rt::kWarps;
+    const int need = (a.units_local + warps_per_cta - 1) / warps_per_cta;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
 
@@ -317,7 +325,7 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     RT_CUDA(cudaMemsetAsync(X.d_stats, 0, rt::kNumStats * sizeof(unsigned long long), stream));
     if (a.compact_out && d_rgba) RT_CUDA(cudaMemsetAsync(d_rgba, 0, (size_t)L.shard_bytes, stream));
     RT_CUDA(cudaEventRecord(X.ev0, stream));
-    kern<<<grid, rt::kThreads, S.total, stream>>>(a);
+    kern<<<grid, threads, S.total, stream>>>(a);
     RT_CUDA(cudaGetLastError());
     RT_CUDA(cudaEventRecord(X.ev1, stream));
     if (use_const) {

@@ -394,6 +394,11 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R, kSrc>::kMinBlocks) r
 #ifndef RT_WAVE_REGEN
 #define RT_WAVE_REGEN 24
 #endif
+#ifndef RT_WAVE_WARPS
+#define RT_WAVE_WARPS 4
+#endif
+constexpr int kWaveWarps = RT_WAVE_WARPS;             // warps per CTA of the wavefront kernel (they never synchronise)
+constexpr int kWaveThreads = 32 * kWaveWarps;
 constexpr int kPool = RT_WAVE_POOL;        // path records per warp
 constexpr int kRegenMin = RT_WAVE_REGEN;   // free records are refilled in batches of at least this many (a regeneration
                                            // round costs the same for 2 lanes as for 32), so (kPool - kRegenMin) / 2 >= 32
@@ -426,20 +431,20 @@ struct WaveSmem { uint32_t acc_off, state_off, meta_off, bt_off, bk_off, self_of
 __host__ __device__ inline WaveSmem wave_smem() {
     WaveSmem L;
     L.acc_off = 0;
-    L.state_off = L.acc_off + kWarps * 2 * kTilePix * 3 * 8;
-    L.meta_off = L.state_off + kWarps * 6 * kPool * 8;
-    L.bt_off = L.meta_off + kWarps * kPool * 16;
-    L.bk_off = L.bt_off + kWarps * kPool * 8;
-    L.self_off = L.bk_off + kWarps * kPool * 4;
-    L.q_off = L.self_off + kWarps * kPool * 4;
-    L.total = L.q_off + kWarps * 3 * kPool;
+    L.state_off = L.acc_off + kWaveWarps * 2 * kTilePix * 3 * 8;
+    L.meta_off = L.state_off + kWaveWarps * 6 * kPool * 8;
+    L.bt_off = L.meta_off + kWaveWarps * kPool * 16;
+    L.bk_off = L.bt_off + kWaveWarps * kPool * 8;
+    L.self_off = L.bk_off + kWaveWarps * kPool * 4;
+    L.q_off = L.self_off + kWaveWarps * kPool * 4;
+    L.total = L.q_off + kWaveWarps * 3 * kPool;
     return L;
 }
 
 #ifndef RT_WAVE_MINB
 #define RT_WAVE_MINB 4   // 128 registers: at 5 CTAs/SM (96) the two phases spill ~230 bytes and run 12 % slower
 #endif
-__global__ void __launch_bounds__(kThreads, RT_WAVE_MINB) render_wave_kernel(const __grid_constant__ RenderArgs a) {
+__global__ void __launch_bounds__(kWaveThreads, RT_WAVE_MINB) render_wave_kernel(const __grid_constant__ RenderArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const WaveSmem L = wave_smem();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

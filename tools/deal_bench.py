@@ -23,7 +23,7 @@ def main():
             for mode_name, mode in (("scan", rt.SCAN_FILTERED), ("auto", rt.SCAN_AUTO)):
                 warm = b.params(mode, False, spp=max(world, wl["spp"] // 32))
                 leg = b.timed(b.params(mode, False), 2 if name != "c5" else 1, 1, flush, warm_p=warm)
-                k = torch.tensor([leg["kernel_ms"] / leg["steps"]], dtype=torch.float64, device=dev)
+                k = torch.tensor([leg["kernel_ms_this_rank"] / leg["steps"]], dtype=torch.float64, device=dev)
                 ks = [torch.zeros_like(k) for _ in range(world)]
                 if world > 1:
                     dist.all_gather(ks, k)
