@@ -4,6 +4,7 @@
 #include "rt_bvh.h"
 #include "rt_kernels.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <atomic>
 #include <mutex>
@@ -79,6 +80,7 @@ struct rt_scene {
     bool cull_ok = true;   // every sphere finite and of moderate magnitude: the FP32 cull is usable
     uint64_t filt_generation = 0;     // version of d_filt (the constant bank caches the last one it was given)
     float4* d_filt = nullptr;
+    float4* d_filt_pk = nullptr;      // the same entries in pairs (rt_device.cuh: cull_scan_packed), what the constant bank holds
     double4* d_exact = nullptr;
     double* d_inv_r = nullptr;        // RN(1/r) per sphere
     float4* d_bvh_nodes = nullptr;    // flattened BVH (rt_bvh.h), built at upload
@@ -265,7 +267,7 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
         ConstBankGuard::Dev& B = g_const_bank.dev[sc->device & 63];
         if (B.owner != sc || B.generation != sc->filt_generation) {
             for (auto& u : B.users) RT_CUDA(cudaStreamWaitEvent(stream, u.second, 0));
-            RT_CUDA(cudaMemcpyToSymbolAsync(rt::c_filt, sc->d_filt, (size_t)(sc->npad + rt::kScanPad) * sizeof(float4), 0,
+            RT_CUDA(cudaMemcpyToSymbolAsync(rt::c_filt, RT_SCAN_PACKED ? sc->d_filt_pk : sc->d_filt, (size_t)(sc->npad + rt::kScanPad) * sizeof(float4), 0,
                                             cudaMemcpyDeviceToDevice, stream));
             // (the events stay in the list: a later copy by another scene must still wait for those kernels; entries of
             //  this stream are overwritten below)
@@ -292,20 +294,43 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     // Work units = (tile, sample chunk).  A launch ends with about one unit's duration of ramp-down, so units should be
     // short -- but a warp holds only two units at a time, and a unit whose last paths are still bouncing blocks the
     // hand-out of the next one.  Measured on an eighth of the C3 frame (tools/chunk_probe.py, profiles/r2_chunk_probe.txt):
-    // the linear-scan kernel (64 paths per warp) is best at 4 samples per pixel and unit (0.995 of the full-frame rate;
-    // 8: 0.990, 2: 0.977), the wavefront kernel (96 records per warp) at 16 (0.956; 8: 0.946, 4: 0.89).  reserved[1]
-    // overrides (tests).
+    // the linear-scan kernel (64 paths per warp) is best at 4 samples per pixel and unit (8: -0.5 %, 2: -1.8 %), the
+    // wavefront kernel (96 records per warp) at 16 (8: -1 %, 4: -7 %).  So the chunks are GRADED: most of a tile's samples
+    // go out in chunks of that efficient length c0, and the launch ends on a level of 4x shorter ones that holds half a
+    // long unit of work per warp -- what it takes to even out the warps' last long units, which end spread over one
+    // long unit's duration.  (A second, again 4x shorter level was measured and costs more than it evens out.)
+    // Levels: lv 0 = the long chunks, lv 1 = one chunk with what does not fill a long one, lv 2 = the short chunks.
+    // reserved[1] > 0 fixes the number of (equal) chunks per tile, -1 keeps the automatic length ungraded, -(10 + F)
+    // sizes the short level at F/4 long units per warp (tests, A/B).
     const int warps_per_cta = threads / 32;
     const int warps = full_grid * warps_per_cta;
     const bool wave = mode == RT_SCAN_BVH && p->reserved[2] != 2;
     const int min_chunk_spp = wave ? 16 : 4, units_per_warp = wave ? 64 : 256;
-    int chunks = (units_per_warp * warps + a.tiles_local - 1) / (a.tiles_local > 0 ? a.tiles_local : 1);
+    const int tiles = a.tiles_local > 0 ? a.tiles_local : 1;
+    int chunks = (int)std::min<long long>(((long long)units_per_warp * warps + tiles - 1) / tiles, 1 << 20);
     const int max_chunks = (p->spp + min_chunk_spp - 1) / min_chunk_spp;
     if (chunks > max_chunks) chunks = max_chunks;
     if (p->reserved[1] > 0) chunks = p->reserved[1] < p->spp ? p->reserved[1] : p->spp;
     if (chunks < 1) chunks = 1;
-    a.chunk_spp = (p->spp + chunks - 1) / chunks;
-    a.chunks = (p->spp + a.chunk_spp - 1) / a.chunk_spp;  // no empty chunk
+    const int c0 = (p->spp + chunks - 1) / chunks;
+    for (int l = 0; l < 3; ++l) { a.lv_n[l] = 0; a.lv_spp[l] = 1; }
+    a.lv_spp[0] = c0;
+    const int quarters = p->reserved[1] <= -11 ? std::min(9, -p->reserved[1] - 10) : 2;
+    // (a progressive pass is followed by the next one on the other stream, which fills its ramp-down: not graded)
+    if (p->reserved[1] > 0 || p->reserved[1] == -1 || c0 < 2 || (d_frame_accum && p->reserved[1] == 0)) {
+        a.lv_n[0] = (p->spp + c0 - 1) / c0;  // no empty chunk
+    } else {
+        const int c1 = std::max(1, c0 / 4);
+        long long t1 = ((long long)quarters * warps * c0 + 4ll * tiles - 1) / (4ll * tiles);   // samples per pixel of the short level
+        t1 = std::min<long long>((t1 + c1 - 1) / c1 * c1, p->spp);
+        const int long_total = p->spp - (int)t1, rem = long_total % c0;
+        int short_total = (int)t1;
+        a.lv_n[0] = long_total / c0;
+        if (rem > c1) { a.lv_n[1] = 1; a.lv_spp[1] = rem; } else short_total += rem;
+        a.lv_spp[2] = c1;
+        a.lv_n[2] = (short_total + c1 - 1) / c1;   // (the very last chunk may be shorter)
+    }
+    a.chunks = a.lv_n[0] + a.lv_n[1] + a.lv_n[2];
     a.units_local = a.tiles_local * a.chunks;
     int grid = full_grid;
     const int need = (a.units_local + warps_per_cta - 1) / warps_per_cta;
@@ -404,6 +429,14 @@ int fill_scene(rt_scene* sc, const double* centres_xyz, const double* radii, boo
     for (int k = 0; k < n; ++k)
         sph[k] = make_float4((float)centres_xyz[3 * k], (float)centres_xyz[3 * k + 1], (float)centres_xyz[3 * k + 2], (float)std::fabs(radii[k]));
     if (cudaMemcpy(sc->d_sph32, sph.data(), sph.size() * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess) return RT_ERR_CUDA;
+    {   // pair-packed copy: spheres 2j, 2j+1 -> {cx,cx',cy,cy'} {cz,cz',w,w'}  (npad + kScanPad is even)
+        std::vector<float4> pk(filt.size());
+        for (size_t j = 0; j + 1 < filt.size(); j += 2) {
+            pk[j] = make_float4(filt[j].x, filt[j + 1].x, filt[j].y, filt[j + 1].y);
+            pk[j + 1] = make_float4(filt[j].z, filt[j + 1].z, filt[j].w, filt[j + 1].w);
+        }
+        if (cudaMemcpy(sc->d_filt_pk, pk.data(), pk.size() * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess) return RT_ERR_CUDA;
+    }
     if (cudaMemcpy(sc->d_filt, filt.data(), filt.size() * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(sc->d_exact, exact.data(), exact.size() * sizeof(double4), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(sc->d_inv_r, inv_r.data(), inv_r.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
@@ -497,6 +530,7 @@ int rt_upload_scene(const double* centres_xyz, const double* radii, int32_t n, i
     do {
         const size_t nf = (size_t)sc->npad + rt::kScanPad, ne = (size_t)(n > 0 ? n : 1);
         if (cudaMalloc(&sc->d_filt, nf * sizeof(float4)) != cudaSuccess ||
+            cudaMalloc(&sc->d_filt_pk, nf * sizeof(float4)) != cudaSuccess ||
             cudaMalloc(&sc->d_exact, ne * sizeof(double4)) != cudaSuccess ||
             cudaMalloc(&sc->d_inv_r, ne * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&sc->d_sph32, ne * sizeof(float4)) != cudaSuccess ||
@@ -528,7 +562,7 @@ void rt_free_scene(rt_scene* sc) {
     if (!sc) return;
     DeviceGuard guard(sc->device);
     if (sc->pending) cudaEventSynchronize(sc->scr.ev1);
-    cudaFree(sc->d_filt); cudaFree(sc->d_exact); cudaFree(sc->d_inv_r);
+    cudaFree(sc->d_filt); cudaFree(sc->d_filt_pk); cudaFree(sc->d_exact); cudaFree(sc->d_inv_r);
     cudaFree(sc->d_bvh_nodes); cudaFree(sc->d_bvh_leaf); cudaFree(sc->d_sph32); cudaFree(sc->d_tie_cells);
     cudaFree(sc->d_frame); cudaFree(sc->d_sum);
     sc->scr.destroy();

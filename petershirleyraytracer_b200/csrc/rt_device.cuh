@@ -137,7 +137,11 @@ struct RenderArgs {
     uint32_t key0, key1;
     int jitter, early_out, scan_mode;
     int tiles_x, tiles_total, shard_rank, shard_count, tiles_local;
-    int chunks, chunk_spp, units_local;  // sample chunks per tile; units = tiles_local * chunks
+    // Work units = (tile, sample chunk).  A tile's samples are cut into GRADED chunks: lv_n[0] chunks of lv_spp[0] samples
+    // per pixel, then lv_n[1] of lv_spp[1], then lv_n[2] of lv_spp[2] (the very last chunk may be shorter); unit ids are
+    // level-major (every tile's long chunks first), so a launch ends on short units (rt_api.cu: launch_render).
+    int chunks, units_local;       // chunks per tile over all levels; units = tiles_local * chunks
+    int lv_n[3], lv_spp[3];
     int compact_out;
     uchar4* out;
     double* sum_out;               // optional W*H*3
@@ -297,6 +301,102 @@ __device__ __forceinline__ void cull_scan(const float4* __restrict__ s_filt, int
                 // 12-bit pass mask without branches (one compare + one select per entry), then one loop over
                 // the set bits (list order).  The straightforward "if (pass) append" per entry compiles to 24
                 // tiny divergent regions per step, which held 16 % of the kernel's warp-state samples.
+                uint32_t pm = 0u;
+#pragma unroll
+                for (int u = 0; u < kScanStep; ++u) pm |= (D[r][u] < f[r].o2) ? 0u : (1u << u);
+                while (pm) {
+                    const int u = __ffs((int)pm) - 1;
+                    pm &= pm - 1u;
+                    if (cnt[r] < kCandCap) {
+                        cand[(cnt[r] * R + r) * stride] = (uint16_t)(kv + u);
+                        ++cnt[r];
+                    } else {
+                        ovf[r] = true;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- packed FP32 (fma.rn.f32x2, SASS FFMA2) form of the constant-bank scan: one instruction evaluates one FMA of the
+// test for TWO spheres.  The bank then holds the entries in pairs -- for spheres 2j, 2j+1 four 64-bit words
+// {cx,cx'} {cy,cy'} {cz,cz'} {w,w'} (rt_api.cu: fill_scene) -- so that one LDCU.64 brings an operand pair into an aligned
+// uniform-register pair, and the lane keeps its ray constants duplicated in both halves of vector-register pairs.
+// Same arithmetic per half as cull_D (each half is an IEEE FP32 fma), same D, same survivors.
+#ifndef RT_SCAN_PACKED
+#define RT_SCAN_PACKED 1   // 0: the scalar FFMA scan (round 1), kept for A/B
+#endif
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 pack2(float x, float y) { u64 d; asm("mov.b64 %0, {%1,%2};" : "=l"(d) : "f"(x), "f"(y)); return d; }
+__device__ __forceinline__ void unpack2(u64 v, float& x, float& y) { asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+struct CullRay2 { u64 dx, dy, dz, ndo, mx, my, mz; };
+__device__ __forceinline__ CullRay2 dup_cull_ray(const CullRay& f) {
+    CullRay2 g;
+    g.dx = pack2(f.dx, f.dx); g.dy = pack2(f.dy, f.dy); g.dz = pack2(f.dz, f.dz); g.ndo = pack2(f.ndo, f.ndo);
+    g.mx = pack2(f.mx, f.mx); g.my = pack2(f.my, f.my); g.mz = pack2(f.mz, f.mz);
+    return g;
+}
+struct CullPair { u64 x, y, z, w; };
+__device__ __forceinline__ void cull_D2(const CullRay2& f, const CullPair& s, float& D0, float& D1) {
+    u64 b = fma2(f.dz, s.z, f.ndo);
+    b = fma2(f.dy, s.y, b);
+    b = fma2(f.dx, s.x, b);
+    u64 D = fma2(b, b, s.w);
+    D = fma2(f.mx, s.x, D);
+    D = fma2(f.my, s.y, D);
+    D = fma2(f.mz, s.z, D);
+    unpack2(D, D0, D1);
+}
+__device__ __forceinline__ CullPair load_pair(int j) {   // pair j = entries 2j, 2j+1 of the (pair-packed) constant bank
+    const u64* p = reinterpret_cast<const u64*>(c_filt) + 4 * j;
+    CullPair s;
+    s.x = p[0]; s.y = p[1]; s.z = p[2]; s.w = p[3];
+    return s;
+}
+template <int R>
+__device__ __forceinline__ void cull_scan_packed(int npad, const CullRay (&f)[R], uint16_t* cand, int stride, int (&cnt)[R],
+                                                 bool (&ovf)[R]) {
+    int kv;
+    asm volatile("mov.u32 %0, 0;" : "=r"(kv));
+    CullRay2 f2[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) f2[r] = dup_cull_ray(f[r]);
+    CullPair g0[2], g1[2], g2[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) { g0[u] = load_pair(u); g1[u] = load_pair(2 + u); }
+#pragma unroll 1
+    for (int k = 0; k < npad; k += kScanStep, kv += kScanStep) {
+        float D[R][kScanStep];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) g2[u] = load_pair(k / 2 + 4 + u);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) cull_D2(f2[r], g0[u], D[r][2 * u], D[r][2 * u + 1]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) g0[u] = load_pair(k / 2 + 6 + u);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) cull_D2(f2[r], g1[u], D[r][4 + 2 * u], D[r][4 + 2 * u + 1]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) g1[u] = load_pair(k / 2 + 8 + u);
+        bool any = false;
+        float m[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) cull_D2(f2[r], g2[u], D[r][8 + 2 * u], D[r][8 + 2 * u + 1]);
+            m[r] = fmax3(fmax3(fmax3(D[r][0], D[r][1], D[r][2]), fmax3(D[r][3], D[r][4], D[r][5]), fmax3(D[r][6], D[r][7], D[r][8])),
+                         fmax3(D[r][9], D[r][10], D[r][11]), D[r][0]);
+            any |= !(m[r] < f[r].o2);
+        }
+        if (any) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (m[r] < f[r].o2) continue;
                 uint32_t pm = 0u;
 #pragma unroll
                 for (int u = 0; u < kScanStep; ++u) pm |= (D[r][u] < f[r].o2) ? 0u : (1u << u);

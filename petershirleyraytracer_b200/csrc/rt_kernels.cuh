@@ -51,8 +51,8 @@ __host__ __device__ inline BatchSmem batch_smem(int npad) {
     return L;
 }
 
-// A work unit = (tile, sample chunk): the 8x8 tile `tile_l` (shard-local index) for samples
-// [chunk*chunk_spp, min(spp, (chunk+1)*chunk_spp)) of every pixel.  Warp-uniform.
+// A work unit = (tile, sample chunk): the 8x8 tile `tile_l` (shard-local index) for the samples of the tile's
+// chunk `chunk` (chunk_first_sample / unit_spp) of every pixel.  Warp-uniform.
 struct Unit {
     int valid;
     int tile_l, chunk;
@@ -68,8 +68,27 @@ __device__ __forceinline__ TileGeom tile_geom(const RenderArgs& a, int tile_l) {
     g.tw = min(kTileW, a.W - g.x0); g.th = min(kTileH, a.H - g.y0);
     return g;
 }
+// Graded chunks (RenderArgs::lv_n / lv_spp): unit id -> (tile, chunk of that tile), chunk -> first sample and length.
+__device__ __forceinline__ void unit_of(const RenderArgs& a, unsigned id, int& tile_l, int& chunk) {
+    const unsigned e0 = (unsigned)a.tiles_local * (unsigned)a.lv_n[0], e1 = e0 + (unsigned)a.tiles_local * (unsigned)a.lv_n[1];
+    unsigned j = id, n = (unsigned)a.lv_n[0];
+    int first = 0;
+    if (id >= e0) { j = id - e0; n = (unsigned)a.lv_n[1]; first = a.lv_n[0]; }
+    if (id >= e1) { j = id - e1; n = (unsigned)a.lv_n[2]; first = a.lv_n[0] + a.lv_n[1]; }
+    const unsigned t = j / n;
+    tile_l = (int)t;
+    chunk = first + (int)(j - t * n);
+}
+__device__ __forceinline__ int chunk_first_sample(const RenderArgs& a, int chunk) {
+    const int k1 = chunk - a.lv_n[0], k2 = k1 - a.lv_n[1];
+    if (k1 < 0) return chunk * a.lv_spp[0];
+    if (k2 < 0) return a.lv_n[0] * a.lv_spp[0] + k1 * a.lv_spp[1];
+    return a.lv_n[0] * a.lv_spp[0] + a.lv_n[1] * a.lv_spp[1] + k2 * a.lv_spp[2];
+}
 __device__ __forceinline__ int unit_spp(const RenderArgs& a, int chunk) {
-    return min(a.chunk_spp, a.spp - chunk * a.chunk_spp);
+    const int k1 = chunk - a.lv_n[0], k2 = k1 - a.lv_n[1];
+    const int len = k1 < 0 ? a.lv_spp[0] : (k2 < 0 ? a.lv_spp[1] : a.lv_spp[2]);
+    return min(len, a.spp - chunk_first_sample(a, chunk));
 }
 
 // write_color's arithmetic (programs/color.h:16-23) for the pixels of a finished tile; coalesced uchar4 rows.
@@ -273,8 +292,7 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R, kSrc>::kMinBlocks) r
                     id = __shfl_sync(0xffffffffu, id, 0);
                     if (__any_sync(0xffffffffu, id >= (unsigned)a.units_local)) { no_more = true; break; }
                     c.valid = 1;
-                    c.tile_l = (int)(id / (unsigned)a.chunks);
-                    c.chunk = (int)(id - (unsigned)c.tile_l * (unsigned)a.chunks);
+                    unit_of(a, id, c.tile_l, c.chunk);
                     const TileGeom g = tile_geom(a, c.tile_l);
                     c.total = (uint32_t)(g.tw * g.th) * (uint32_t)unit_spp(a, c.chunk);
                     c.next = 0;
@@ -288,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R, kSrc>::kMinBlocks) r
                     const uint32_t id = c.next + rank;
                     const uint32_t ns = (uint32_t)unit_spp(a, c.chunk);
                     const uint32_t p = id / ns;
-                    const uint32_t s = (uint32_t)(a.sample_base + c.chunk * a.chunk_spp) + (id - p * ns);
+                    const uint32_t s = (uint32_t)(a.sample_base + chunk_first_sample(a, c.chunk)) + (id - p * ns);
                     const int ly = (int)p / g.tw, lx = (int)p - ly * g.tw;
                     const int i = g.x0 + lx, j = a.H - 1 - (g.y0 + ly);  // j from the bottom (programs/main.cc:72)
                     const uint32_t pixid = (uint32_t)(j * a.W + i);
@@ -355,7 +373,10 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R, kSrc>::kMinBlocks) r
                 ovf[r] = live && (a.scan_mode != 0 || !sane);
             }
         }
-        if (!kBvh && a.scan_mode == 0) cull_scan<R, kConst>(s_filt, a.sc.npad, f, cand, kThreads, cnt, ovf);
+        if (!kBvh && a.scan_mode == 0) {
+            if (RT_SCAN_PACKED && kConst) cull_scan_packed<R>(a.sc.npad, f, cand, kThreads, cnt, ovf);
+            else cull_scan<R, kConst>(s_filt, a.sc.npad, f, cand, kThreads, cnt, ovf);
+        }
         cntpack = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) cntpack |= ((uint32_t)cnt[r] | (ovf[r] ? 0x80u : 0u)) << (8 * r);
@@ -495,11 +516,10 @@ __global__ void __launch_bounds__(kWaveThreads, RT_WAVE_MINB) render_wave_kernel
                 id = __shfl_sync(0xffffffffu, id, 0);
                 if (id >= (unsigned)a.units_local) { no_more = true; break; }
                 c.valid = 1;
-                c.tile_l = (int)(id / (unsigned)a.chunks);
-                c.chunk = (int)(id - (unsigned)c.tile_l * (unsigned)a.chunks);
+                unit_of(a, id, c.tile_l, c.chunk);
                 geo = tile_geom(a, c.tile_l);
                 unit_ns = (uint32_t)unit_spp(a, c.chunk);
-                unit_s0 = (uint32_t)(a.sample_base + c.chunk * a.chunk_spp);
+                unit_s0 = (uint32_t)(a.sample_base + chunk_first_sample(a, c.chunk));
                 c.total = (uint32_t)(geo.tw * geo.th) * unit_ns;
                 c.next = 0;
                 cur = np;

@@ -22,19 +22,23 @@ def test_library_targets_sm_100a(rt):
 
 
 def test_default_render_kernel_scans_on_the_uniform_datapath(rt):
-    """The cull entries must be loaded with LDCU (uniform registers) from constant bank 3 and consumed as
-    FFMA R, R, UR, R.  ptxas drops to vector LDC + three-register FFMAs (63% rate on B200, see
-    tools/microbench.cu) for seemingly unrelated source changes -- e.g. a second __syncwarp() in the main
-    loop or storing the loop counter -- so this is pinned here."""
+    """The cull entries must be loaded with LDCU.64 (aligned uniform-register pairs) from constant bank 3 and consumed
+    by packed FFMA2 (fma.rn.f32x2: one instruction = one FMA of the test for two spheres) as
+    FFMA2 R, R.F32, UR.F32x2, R -- the lane's ray constant broadcast from ONE register, the sphere pair from the
+    uniform pair.  ptxas drops to vector LDC + three-register-pair FFMA2 (62% rate on B200, see tools/microbench2.cu)
+    for seemingly unrelated source changes -- e.g. a second __syncwarp() in the main loop or storing the loop
+    counter -- so this is pinned here."""
     s = _sass(rt, "_ZN2rt13render_kernelILi2ELi1EEEvNS_10RenderArgsE")
-    ldcu = len(re.findall(r"LDCU(\.\d+)? UR\d+, c\[0x3\]", s))
+    ldcu = len(re.findall(r"LDCU\.64 UR\d+, c\[0x3\]", s))
     ldc_vec = len(re.findall(r"LDC(\.\d+)? R\d+, c\[0x3\]\[R", s))
-    ffma_ur = len(re.findall(r"FFMA R\d+, [^;]*UR\d+", s))
-    ffma = len(re.findall(r"\bFFMA\b", s))
-    assert ldcu >= 16 and ldc_vec == 0, (ldcu, ldc_vec)
-    # every FFMA of the cull formula has exactly one per-sphere operand (multiplicand or addend), so none of the
-    # entry constants is moved into a vector register
-    assert ffma_ur >= 0.9 * ffma, (ffma_ur, ffma)
+    ffma2 = len(re.findall(r"\bFFMA2\b", s))
+    ffma2_ur = len(re.findall(r"FFMA2 R\d+, [^;]*UR\d+\.F32x2", s))
+    ffma2_bcast = len(re.findall(r"FFMA2 R\d+, R\d+(\.reuse)?\.F32,", s))
+    assert ldcu >= 24 and ldc_vec == 0, (ldcu, ldc_vec)
+    # 2 rays x 6 sphere pairs x 7 FMAs per scan step; every one has exactly one per-sphere operand (multiplicand or
+    # addend) and takes it from a uniform-register pair; the ray constants are never duplicated into register pairs
+    assert ffma2 == 84 and ffma2_ur == 84, (ffma2, ffma2_ur)
+    assert ffma2_bcast >= 72, ffma2_bcast     # (the 12 b*b + w FMAs square a register pair)
     assert "FMNMX3" in s          # 3-input max of the per-step pass test
     assert "STL" not in s and "LDL" not in s   # no register spills in the hot kernel
 

@@ -248,6 +248,23 @@ def test_render_modes_agree_bitwise(rt, book):
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("mode", [0, 2])
+def test_graded_work_units_do_not_change_the_frame(rt, book, mode):
+    """A frame large enough that launch_render cuts every tile's samples into all three levels of graded chunks
+    (long units first, the launch ends on short ones) equals the single-chunk and the ungraded renders bit for bit:
+    the sums are integers and every (pixel, sample) keys its own Philox stream (rt_api.cu: launch_render)."""
+    from petershirleyraytracer_b200 import scenes
+    c, r = book
+    W, H, spp = 800, 600, 48
+    cam = scenes.book_camera(W, H)
+    base, bsum, bst = _render_both(rt, c, r, cam, W, H, spp, 50, 4, scan_mode=mode)            # graded (automatic)
+    for kw in (dict(chunks=1), dict(chunks=-1), dict(chunks=7)):
+        img, sm, st = _render_both(rt, c, r, cam, W, H, spp, 50, 4, scan_mode=mode, **kw)
+        assert np.array_equal(img, base), kw
+        assert np.array_equal(bits(sm), bits(bsum)), kw
+        assert st["samples"] == bst["samples"] == W * H * spp and st["casts"] == bst["casts"], kw
+
+
 def test_render_depth_edge_cases(rt, book):
     from petershirleyraytracer_b200 import scenes
     c, r = book

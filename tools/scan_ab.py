@@ -1,0 +1,23 @@
+"""A/B of linear-scan kernel builds (RT_B200_LIB selects the library): kernel-time Msamples/s on C3 at reference semantics
+for R = 2 and R = 4 paths per lane, plus the frame's md5 (every build must print the same one)."""
+import sys, os, json, hashlib
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import petershirleyraytracer_b200 as rt
+from petershirleyraytracer_b200 import scenes
+
+spp = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+c, r = scenes.book_scene(11)
+W, H = 1200, 800
+cam = scenes.book_camera(W, H)
+with rt.Scene(c, r) as sc:
+    for kw in (dict(), dict(paths_per_lane=4), dict(paths_per_lane=1), dict(early_out=True), dict(tmin=0.001)):
+        args = dict(early_out=False)
+        args.update(kw)
+        p = rt.make_params(W, H, spp, 50, seed=1, scan_mode=0, **args)
+        best = None
+        for _ in range(3):
+            rgba, _, st = rt.render(sc, cam, p)
+            if best is None or st["kernel_ms"] < best["kernel_ms"]:
+                best = st
+        print(json.dumps(dict(kw=kw, ms=round(best["kernel_ms"], 2), msamples_s=round(best["samples"] / best["kernel_ms"] / 1e3, 1),
+                              md5=hashlib.md5(rgba.tobytes()).hexdigest()[:12])), flush=True)
