@@ -12,6 +12,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -450,10 +451,18 @@ int fill_scene(rt_scene* sc, const double* centres_xyz, const double* radii, boo
         return RT_OK;
     }
     const bool have_tree = sc->d_bvh_nodes && !sc->bvh_host.nodes.empty();
+    // tie grid (start-sphere fast path of the BVH mode), rebuilt for the current positions: independent of the tree, so
+    // it is built on a thread of its own while this one (and, for large scenes, the builder's threads) does the tree
+    std::thread tie_thread;
+    int host_threads = 0;   // 0: what the host offers
+    if (const char* e = std::getenv("RT_HOST_THREADS")) host_threads = std::atoi(e);   // tuning experiments only (1: sequential build)
+    if (n >= 4096 && host_threads != 1) tie_thread = std::thread([&] { rt::build_tie_grid(centres_xyz, radii, n, &sc->tie); });
+    else rt::build_tie_grid(centres_xyz, radii, n, &sc->tie);
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{tie_thread};   // (also on the error returns)
     if (refit && have_tree) {
         rt::refit_bvh(centres_xyz, radii, &sc->bvh_host);
     } else {
-        rt::build_bvh(centres_xyz, radii, n, &sc->bvh_host);
+        rt::build_bvh(centres_xyz, radii, n, &sc->bvh_host, host_threads);
     }
     const rt::BvhHost& bvh = sc->bvh_host;
     const size_t nb = bvh.nodes4.size() * sizeof(rt::Bvh4Node), lb = (bvh.leaf_idx.size() + 1) * sizeof(int32_t);
@@ -467,8 +476,7 @@ int fill_scene(rt_scene* sc, const double* centres_xyz, const double* radii, boo
     if (!bvh.leaf_idx.empty() &&
         cudaMemcpy(sc->d_bvh_leaf, bvh.leaf_idx.data(), bvh.leaf_idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess)
         return RT_ERR_CUDA;
-    // tie grid (start-sphere fast path of the BVH mode), rebuilt for the current positions
-    rt::build_tie_grid(centres_xyz, radii, n, &sc->tie);
+    if (tie_thread.joinable()) tie_thread.join();
     if (sc->tie.ok) {
         const size_t cb = sc->tie.cells.size() * sizeof(int32_t);
         if (cb > sc->tie_cells_cap) {

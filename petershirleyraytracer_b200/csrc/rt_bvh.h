@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <thread>
 #include <vector>
 
 namespace rt {
@@ -73,7 +74,7 @@ inline void empty_box(float* lo, float* hi) {
 
 struct Builder {
     const double* c; const double* r;
-    std::vector<int32_t> order;
+    std::vector<int32_t>& order;   // sphere indices; a (sub)tree permutes only its own range, so subtrees build in parallel
     BvhHost* out;
 
     Box bounds(int first, int count) const {
@@ -170,8 +171,10 @@ struct Builder {
         return (left > 0 && left < count) ? left : 0;
     }
 
-    // returns the child reference for spheres order[first, first+count)
-    int32_t build(int first, int count, int depth = 0) {
+    // returns the child reference for spheres order[first, first+count); nodes are appended to `nodes` in pre-order
+    // (parent, left subtree, right subtree).  While fork > 0 the left subtree is built by another thread into a vector
+    // of its own and spliced in behind the parent -- the same array, index for index, as the sequential build.
+    int32_t build(std::vector<BvhNode>& nodes, int first, int count, int depth = 0, int fork = 0) {
         if (kBvhLeafMax == 1 && count == 1) {
             // single-sphere leaves name their sphere directly (leaf_idx is the identity): the device skips the
             // leaf-list load, a dependent fetch in front of every FP64 sphere test
@@ -200,12 +203,35 @@ struct Builder {
             std::nth_element(order.begin() + first, order.begin() + first + mid, order.begin() + first + count,
                              [&](int32_t x, int32_t y) { return c[3 * x + axis] < c[3 * y + axis]; });
         }
-        const int32_t me = (int32_t)out->nodes.size();
-        out->nodes.push_back(BvhNode{});
-        const Box b0 = bounds(first, mid), b1 = bounds(first + mid, count - mid);
-        const int32_t c0 = build(first, mid, depth + 1);
-        const int32_t c1 = build(first + mid, count - mid, depth + 1);
-        BvhNode& n = out->nodes[me];
+        const int32_t me = (int32_t)nodes.size();
+        nodes.push_back(BvhNode{});
+        int32_t c0, c1;
+        Box b0, b1;
+        if (fork > 0 && kBvhLeafMax == 1 && count >= 4096) {
+            std::vector<BvhNode> left;
+            int32_t c0_local = 0;
+            std::thread th([&] { b0 = bounds(first, mid); c0_local = build(left, first, mid, depth + 1, fork - 1); });
+            b1 = bounds(first + mid, count - mid);
+            std::vector<BvhNode> right;
+            const int32_t c1_local = build(right, first + mid, count - mid, depth + 1, fork - 1);
+            th.join();
+            auto splice = [&](std::vector<BvhNode>& sub, int32_t ref) {
+                const int32_t off = (int32_t)nodes.size();
+                for (BvhNode& n : sub) {
+                    if (n.child0 >= 0) n.child0 += off;
+                    if (n.child1 >= 0) n.child1 += off;
+                }
+                nodes.insert(nodes.end(), sub.begin(), sub.end());
+                return ref >= 0 ? ref + off : ref;
+            };
+            c0 = splice(left, c0_local);
+            c1 = splice(right, c1_local);
+        } else {
+            b0 = bounds(first, mid); b1 = bounds(first + mid, count - mid);
+            c0 = build(nodes, first, mid, depth + 1, 0);
+            c1 = build(nodes, first + mid, count - mid, depth + 1, 0);
+        }
+        BvhNode& n = nodes[me];
         store_box(b0, n.lo0, n.hi0);
         store_box(b1, n.lo1, n.hi1);
         n.child0 = c0; n.child1 = c1;
@@ -315,19 +341,20 @@ inline void collapse_bvh4(BvhHost* bvh) {
     }
 }
 
-inline void build_bvh(const double* centres, const double* radii, int n, BvhHost* out) {
+// `threads` <= 0: as many as the host offers (at most 16); the tree does not depend on the thread count.
+inline void build_bvh(const double* centres, const double* radii, int n, BvhHost* out, int threads = 0) {
     using namespace bvh_detail;
     out->nodes.clear(); out->leaf_idx.clear();
-    Builder b{centres, radii, {}, out};
-    b.order.resize(n);
-    for (int i = 0; i < n; ++i) b.order[i] = i;
+    std::vector<int32_t> order((size_t)n);
+    Builder b{centres, radii, order, out};
+    for (int i = 0; i < n; ++i) order[i] = i;
     if (kBvhLeafMax == 1) {  // identity leaf list (see Builder::build)
         out->leaf_idx.resize(n);
         for (int i = 0; i < n; ++i) out->leaf_idx[i] = i;
     }
     if (n <= kBvhLeafMax) {  // root must be a node: one real leaf + one empty child
         out->nodes.push_back(BvhNode{});
-        const int32_t leaf = n > 0 ? b.build(0, n) : (int32_t)0x80000000u;
+        const int32_t leaf = n > 0 ? b.build(out->nodes, 0, n) : (int32_t)0x80000000u;
         BvhNode& root = out->nodes[0];
         if (n > 0) store_box(b.bounds(0, n), root.lo0, root.hi0); else empty_box(root.lo0, root.hi0);
         empty_box(root.lo1, root.hi1);
@@ -335,7 +362,11 @@ inline void build_bvh(const double* centres, const double* radii, int n, BvhHost
         collapse_bvh4(out);
         return;
     }
-    b.build(0, n);  // nodes[0] is the root because the first push_back happens at the top call
+    if (threads <= 0) threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    int fork = 0;
+    while ((1 << fork) < threads) ++fork;   // 2^fork subtrees build concurrently
+    out->nodes.reserve((size_t)n);
+    b.build(out->nodes, 0, n, 0, fork);  // nodes[0] is the root because the first push_back happens at the top call
     collapse_bvh4(out);
 }
 

@@ -4,6 +4,7 @@
 #include "rt_bvh.h"
 
 #include <cstdio>
+#include <cstring>
 #include <random>
 #include <set>
 
@@ -82,6 +83,17 @@ int main() {
         rt::refit_bvh(m.c.data(), m.r.data(), &b);
         CHECK(b.nodes.size() == nodes_before);
         if (check_tree(b, m, "  refit")) return 1;
+    }
+    {   // the threaded build (subtrees on several threads, spliced back in pre-order) is the sequential tree, index for index
+        Scene s; s.c.insert(s.c.end(), {0, -1000, 0}); s.r.push_back(1000);
+        for (int a = -70; a < 70; ++a) for (int b = -70; b < 70; ++b) { s.c.insert(s.c.end(), {a + 0.9 * U(g), 0.2, b + 0.9 * U(g)}); s.r.push_back(0.2); }
+        rt::BvhHost seq, par;
+        rt::build_bvh(s.c.data(), s.r.data(), (int)s.r.size(), &seq, 1);
+        rt::build_bvh(s.c.data(), s.r.data(), (int)s.r.size(), &par, 8);
+        CHECK(seq.nodes.size() == par.nodes.size() && seq.nodes4.size() == par.nodes4.size());
+        CHECK(std::memcmp(seq.nodes.data(), par.nodes.data(), seq.nodes.size() * sizeof(rt::BvhNode)) == 0);
+        CHECK(std::memcmp(seq.nodes4.data(), par.nodes4.data(), seq.nodes4.size() * sizeof(rt::Bvh4Node)) == 0);
+        if (check_tree(par, s, "book 19601, 8 threads")) return 1;
     }
     std::printf("ok\n");
     return 0;

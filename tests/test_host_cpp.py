@@ -9,7 +9,7 @@ def test_flatten_and_api_surface(tmp_path, rt):
     exe = tmp_path / "flatten_test"
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     pkg = os.path.dirname(rt.LIB_PATH)
-    subprocess.run([cxx, "-O1", "-std=c++17", "-I", os.path.join(REPO, "include"), "-I", os.path.join(REPO, "include", "compat"),
+    subprocess.run([cxx, "-O1", "-std=c++17", "-pthread", "-I", os.path.join(REPO, "include"), "-I", os.path.join(REPO, "include", "compat"),
                     os.path.join(REPO, "tests", "cpp", "flatten_test.cc"), "-o", str(exe), "-L", pkg, "-lrt_b200",
                     f"-Wl,-rpath,{pkg}"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
@@ -33,7 +33,7 @@ def test_bvh_builder_invariants(tmp_path):
     property the exact traversal rests on -- for SAH builds of ordinary and adversarial scenes and after a refit."""
     exe = tmp_path / "bvh_host_test"
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.run([cxx, "-O1", "-std=c++17", "-I", os.path.join(REPO, "petershirleyraytracer_b200", "csrc"),
+    subprocess.run([cxx, "-O1", "-std=c++17", "-pthread", "-I", os.path.join(REPO, "petershirleyraytracer_b200", "csrc"),
                     os.path.join(REPO, "tests", "cpp", "bvh_host_test.cc"), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout[-2000:] + out.stderr[-2000:]
@@ -44,7 +44,7 @@ def test_tie_grid_containment(tmp_path):
     giant or listed in the cell the device looks up (ordinary, clustered, nested, coincident and tiny scenes)."""
     exe = tmp_path / "tie_grid_test"
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.run([cxx, "-O1", "-std=c++17", "-I", os.path.join(REPO, "petershirleyraytracer_b200", "csrc"),
+    subprocess.run([cxx, "-O1", "-std=c++17", "-pthread", "-I", os.path.join(REPO, "petershirleyraytracer_b200", "csrc"),
                     os.path.join(REPO, "tests", "cpp", "tie_grid_test.cc"), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout[-2000:] + out.stderr[-2000:]
