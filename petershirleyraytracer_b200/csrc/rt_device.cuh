@@ -591,6 +591,8 @@ __device__ __forceinline__ void bvh_cast(const SceneDev& sc, double ox, double o
         bool hit[W];
 #pragma unroll
         for (int i = 0; i < W; ++i) {
+            // (the 24 slab FMAs as 12 FFMA2 -- child pairs from the float4 quads, 1/d and -o/d broadcast -- measured: 0..-3 %,
+            //  profiles/r2_ab_wave2.txt)
             const float ax = fmaf(lx[i], ivx, clx), bx = fmaf(hx[i], ivx, chx);
             const float ay = fmaf(ly[i], ivy, cly), by = fmaf(hy[i], ivy, chy);
             const float az = fmaf(lz[i], ivz, clz), bz = fmaf(hz[i], ivz, chz);
@@ -679,40 +681,36 @@ __device__ __forceinline__ bool tie_candidate(const float4 s, float fx, float fy
 // The part of a BVH-mode cast that needs no traversal: FP64 sphere::hit of the start sphere, then the tie grid.
 // Returns true if `best` is the cast's final answer; false if the cast cannot be decided here (not a hit of the
 // start sphere, reach too long, overfull cell): the caller traverses with `best` as the initial bound.  (tmax = +inf.)
-// One rolled loop over the candidates -- entry 0 is the start sphere, then the giants, then the cell's spheres -- so
-// that the FP64 test exists once in the instruction stream.
+// One rolled loop over a pending mask -- bit 0 is the start sphere, bits 1-4 the giants, bits 5-8 the cell's spheres --
+// so that the FP64 test exists once in the instruction stream.  The first trip tests the start sphere and then runs the
+// FP32 shell tests of ALL candidates in straight-line code (their loads are in flight together); only candidates that
+// pass (0.3 % of the casts) set their bit and cost another trip.  (Round 2, first form: one trip per candidate, shell
+// test or not -- 4-5 trips per warp and one dependent load each.)
 __device__ __forceinline__ bool self_cast(const SceneDev& sc, int self, double ox, double oy, double oz, double dx,
                                           double dy, double dz, double A, double tmin, Best& best, uint32_t& n_exact) {
     if (self < 0) return false;
     const RcpA dA = make_rcp(A);
     const double kInf = __longlong_as_double(0x7ff0000000000000ll);
     bool decided = false;
-    int ncand = 1;
+    uint32_t pend = 1u;
     int4 cell = make_int4(-1, -1, -1, -1);
-    float fx = 0.f, fy = 0.f, fz = 0.f, o2 = 0.f, rho = 0.f;
 #pragma unroll 1
-    for (int e = 0; e < ncand; ++e) {
+    while (pend) {
+        const int e = __ffs((int)pend) - 1;
+        pend &= pend - 1u;
         int j = self;
-        bool test = true;
-        if (e > 0) {
-            const int g = e - 1 - sc.tie_ngiants;
-            if (g < 0) j = sc.tie_giants[e - 1];
-            else j = g == 0 ? cell.x : (g == 1 ? cell.y : (g == 2 ? cell.z : cell.w));
-            test = j != self && tie_candidate(__ldg(sc.sph32 + j), fx, fy, fz, o2, rho);
-        }
-        if (test) {
-            ++n_exact;
-            exact_test_unordered(sc.exact, j, ox, oy, oz, dx, dy, dz, dA, tmin, kInf, best);
-        }
+        if (e > 0) j = e <= 4 ? sc.tie_giants[e - 1] : (e == 5 ? cell.x : (e == 6 ? cell.y : (e == 7 ? cell.z : cell.w)));
+        ++n_exact;
+        exact_test_unordered(sc.exact, j, ox, oy, oz, dx, dy, dz, dA, tmin, kInf, best);
         if (e == 0) {
             if (!(sc.tie_ok && best.k == self && dA.fast)) break;
+            float rho = 0.f;
             if (best.t != 0.0) {   // reach = t * |dir|, rounded up
                 rho = __fmul_ru(__fmul_ru(__double2float_ru(best.t), __fsqrt_ru(__double2float_ru(A))), 1.0000019f);
                 if (!(rho <= sc.tie_rho_max)) break;   // (also NaN / negative t)
             }
-            fx = (float)ox; fy = (float)oy; fz = (float)oz;
-            o2 = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
-            int ncell = 0;
+            const float fx = (float)ox, fy = (float)oy, fz = (float)oz;
+            const float o2 = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
             const bool inside = fx >= sc.tie_g0[0] && fx <= sc.tie_g1[0] && fy >= sc.tie_g0[1] && fy <= sc.tie_g1[1] &&
                                 fz >= sc.tie_g0[2] && fz <= sc.tie_g1[2];
             if (inside) {   // outside the grid no listed sphere has its (padded) box around o
@@ -720,9 +718,22 @@ __device__ __forceinline__ bool self_cast(const SceneDev& sc, int self, double o
                           iz = (int)((fz - sc.tie_g0[2]) * sc.tie_inv_h);
                 cell = __ldg(sc.tie_cells + ((size_t)iz * sc.tie_dimy + iy) * sc.tie_dimx + ix);
                 if (cell.x == -2) break;   // overfull cell
-                ncell = (cell.x >= 0) + (cell.y >= 0) + (cell.z >= 0) + (cell.w >= 0);   // (entries fill from .x up)
             }
-            ncand = 1 + sc.tie_ngiants + ncell;
+            // the cell's spheres (entries fill from .x up; -1: unused): loads first, they fly while the giants are tested
+            const bool c0 = cell.x >= 0 && cell.x != self, c1 = cell.y >= 0 && cell.y != self, c2 = cell.z >= 0 && cell.z != self,
+                       c3 = cell.w >= 0 && cell.w != self;
+            const float4 never = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, 0.f);   // (|q| = inf: no candidate)
+            const float4 s0 = c0 ? __ldg(sc.sph32 + cell.x) : never, s1 = c1 ? __ldg(sc.sph32 + cell.y) : never,
+                         s2 = c2 ? __ldg(sc.sph32 + cell.z) : never, s3 = c3 ? __ldg(sc.sph32 + cell.w) : never;
+#pragma unroll 1
+            for (int g = 0; g < sc.tie_ngiants; ++g) {   // (warp-uniform trip count)
+                const int jg = sc.tie_giants[g];
+                if (jg != self && tie_candidate(__ldg(sc.sph32 + jg), fx, fy, fz, o2, rho)) pend |= 2u << g;
+            }
+            if (c0 && tie_candidate(s0, fx, fy, fz, o2, rho)) pend |= 32u;
+            if (c1 && tie_candidate(s1, fx, fy, fz, o2, rho)) pend |= 64u;
+            if (c2 && tie_candidate(s2, fx, fy, fz, o2, rho)) pend |= 128u;
+            if (c3 && tie_candidate(s3, fx, fy, fz, o2, rho)) pend |= 256u;
             decided = true;
         }
     }
