@@ -76,7 +76,13 @@ __device__ __forceinline__ void unit_of(const RenderArgs& a, unsigned id, int& t
     if (id >= e0) { j = id - e0; n = (unsigned)a.lv_n[1]; first = a.lv_n[0]; }
     if (id >= e1) { j = id - e1; n = (unsigned)a.lv_n[2]; first = a.lv_n[0] + a.lv_n[1]; }
     const unsigned t = j / n;
-    tile_l = (int)t;
+    // Tiles are handed out from the LAST row of the frame up: a launch's ramp-down is set by the longest paths of its
+    // last units, and the frames of this renderer have their sky (paths of one cast) at the top and the ground with its
+    // trapped paths (51 casts) at the bottom.  (Any order gives the same frame.)
+#ifndef RT_TILE_REVERSE
+#define RT_TILE_REVERSE 1
+#endif
+    tile_l = RT_TILE_REVERSE ? a.tiles_local - 1 - (int)t : (int)t;
     chunk = first + (int)(j - t * n);
 }
 __device__ __forceinline__ int chunk_first_sample(const RenderArgs& a, int chunk) {
