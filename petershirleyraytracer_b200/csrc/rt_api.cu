@@ -292,46 +292,12 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     if (per_sm < 1) return fail(RT_ERR_CUDA, "render kernel does not fit on an SM");
     const int full_grid = sc->sm_count * per_sm;  // persistent: every resident warp pulls work units
 
-    // Work units = (tile, sample chunk).  A launch ends with about one unit's duration of ramp-down, so units should be
-    // short -- but a warp holds only two units at a time, and a unit whose last paths are still bouncing blocks the
-    // hand-out of the next one.  Measured on an eighth of the C3 frame (tools/chunk_probe.py, profiles/r2_chunk_probe.txt):
-    // the linear-scan kernel (64 paths per warp) is best at 4 samples per pixel and unit (8: -0.5 %, 2: -1.8 %), the
-    // wavefront kernel (96 records per warp) at 16 (8: -1 %, 4: -7 %).  So the chunks are GRADED: most of a tile's samples
-    // go out in chunks of that efficient length c0, and the launch ends on a level of 4x shorter ones that holds half a
-    // long unit of work per warp -- what it takes to even out the warps' last long units, which end spread over one
-    // long unit's duration.  (A second, again 4x shorter level was measured and costs more than it evens out.)
-    // Levels: lv 0 = the long chunks, lv 1 = one chunk with what does not fill a long one, lv 2 = the short chunks.
-    // reserved[1] > 0 fixes the number of (equal) chunks per tile, -1 keeps the automatic length ungraded, -(10 + F)
-    // sizes the short level at F/4 long units per warp (tests, A/B).
+    // work units: graded sample chunks per tile (rt_units.h)
     const int warps_per_cta = threads / 32;
     const int warps = full_grid * warps_per_cta;
     const bool wave = mode == RT_SCAN_BVH && p->reserved[2] != 2;
-    const int min_chunk_spp = wave ? 16 : 4, units_per_warp = wave ? 64 : 256;
-    const int tiles = a.tiles_local > 0 ? a.tiles_local : 1;
-    int chunks = (int)std::min<long long>(((long long)units_per_warp * warps + tiles - 1) / tiles, 1 << 20);
-    const int max_chunks = (p->spp + min_chunk_spp - 1) / min_chunk_spp;
-    if (chunks > max_chunks) chunks = max_chunks;
-    if (p->reserved[1] > 0) chunks = p->reserved[1] < p->spp ? p->reserved[1] : p->spp;
-    if (chunks < 1) chunks = 1;
-    const int c0 = (p->spp + chunks - 1) / chunks;
-    for (int l = 0; l < 3; ++l) { a.lv_n[l] = 0; a.lv_spp[l] = 1; }
-    a.lv_spp[0] = c0;
-    const int quarters = p->reserved[1] <= -11 ? std::min(9, -p->reserved[1] - 10) : 2;
-    // (a progressive pass is followed by the next one on the other stream, which fills its ramp-down: not graded)
-    if (p->reserved[1] > 0 || p->reserved[1] == -1 || c0 < 2 || (d_frame_accum && p->reserved[1] == 0)) {
-        a.lv_n[0] = (p->spp + c0 - 1) / c0;  // no empty chunk
-    } else {
-        const int c1 = std::max(1, c0 / 4);
-        long long t1 = ((long long)quarters * warps * c0 + 4ll * tiles - 1) / (4ll * tiles);   // samples per pixel of the short level
-        t1 = std::min<long long>((t1 + c1 - 1) / c1 * c1, p->spp);
-        const int long_total = p->spp - (int)t1, rem = long_total % c0;
-        int short_total = (int)t1;
-        a.lv_n[0] = long_total / c0;
-        if (rem > c1) { a.lv_n[1] = 1; a.lv_spp[1] = rem; } else short_total += rem;
-        a.lv_spp[2] = c1;
-        a.lv_n[2] = (short_total + c1 - 1) / c1;   // (the very last chunk may be shorter)
-    }
-    a.chunks = a.lv_n[0] + a.lv_n[1] + a.lv_n[2];
+    a.up = rt::plan_units(p->spp, a.tiles_local, warps, wave, p->reserved[1], d_frame_accum != nullptr);
+    a.chunks = rt::plan_chunks(a.up);
     a.units_local = a.tiles_local * a.chunks;
     int grid = full_grid;
     const int need = (a.units_local + warps_per_cta - 1) / warps_per_cta;

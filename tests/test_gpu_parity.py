@@ -252,7 +252,7 @@ def test_render_modes_agree_bitwise(rt, book):
 def test_graded_work_units_do_not_change_the_frame(rt, book, mode):
     """A frame large enough that launch_render cuts every tile's samples into all three levels of graded chunks
     (long units first, the launch ends on short ones) equals the single-chunk and the ungraded renders bit for bit:
-    the sums are integers and every (pixel, sample) keys its own Philox stream (rt_api.cu: launch_render)."""
+    the sums are integers and every (pixel, sample) keys its own Philox stream (csrc/rt_units.h)."""
     from petershirleyraytracer_b200 import scenes
     c, r = book
     W, H, spp = 800, 600, 48

@@ -48,3 +48,14 @@ def test_tie_grid_containment(tmp_path):
                     os.path.join(REPO, "tests", "cpp", "tie_grid_test.cc"), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_work_unit_plans_cover_every_sample_once(tmp_path):
+    """rt_units.h on the host: whatever the frame, spp, grid, kernel and tuning knob, the graded chunks of a tile are
+    contiguous, non-empty and add up to spp, and the unit ids of a launch enumerate every (tile, chunk) exactly once."""
+    exe = tmp_path / "units_test"
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-O1", "-std=c++17", "-I", os.path.join(REPO, "petershirleyraytracer_b200", "csrc"),
+                    os.path.join(REPO, "tests", "cpp", "units_test.cc"), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout[-2000:] + out.stderr[-2000:]
