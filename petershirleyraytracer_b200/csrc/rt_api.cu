@@ -286,6 +286,7 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     else if (mode == RT_SCAN_BVH) { kern = rt::render_wave_kernel; S.total = rt::wave_smem().total; threads = rt::kWaveThreads; }
     else if (use_const) kern = R == 1 ? rt::render_kernel<1, 1> : (R == 2 ? rt::render_kernel<2, 1> : rt::render_kernel<4, 1>);
     else kern = R == 1 ? rt::render_kernel<1, 0> : (R == 2 ? rt::render_kernel<2, 0> : rt::render_kernel<4, 0>);
+    if (const char* e = std::getenv("RT_SMEM_PAD")) S.total += (uint32_t)std::atoi(e);   // tuning experiments only: fewer CTAs per SM
     RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
     int per_sm = 0;
     RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, S.total));
