@@ -3,6 +3,7 @@
 #include "../../include/rt.h"
 #include "rt_bvh.h"
 #include "rt_kernels.cuh"
+#include "rt_units.h"
 
 #include <algorithm>
 #include <cmath>
@@ -297,8 +298,9 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     const int warps_per_cta = threads / 32;
     const int warps = full_grid * warps_per_cta;
     const bool wave = mode == RT_SCAN_BVH && p->reserved[2] != 2;
-    a.up = rt::plan_units(p->spp, a.tiles_local, warps, wave, p->reserved[1], d_frame_accum != nullptr);
-    a.chunks = rt::plan_chunks(a.up);
+    const rt::UnitPlan up = rt::plan_units(p->spp, a.tiles_local, warps, wave, p->reserved[1], d_frame_accum != nullptr);
+    for (int l = 0; l < 3; ++l) { a.lv_n[l] = up.lv_n[l]; a.lv_spp[l] = up.lv_spp[l]; }
+    a.chunks = rt::plan_chunks(up);
     a.units_local = a.tiles_local * a.chunks;
     int grid = full_grid;
     const int need = (a.units_local + warps_per_cta - 1) / warps_per_cta;

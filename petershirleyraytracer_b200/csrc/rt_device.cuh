@@ -12,8 +12,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "rt_units.h"
-
 namespace rt {
 
 // ---------------------------------------------------------------- constants
@@ -139,8 +137,11 @@ struct RenderArgs {
     uint32_t key0, key1;
     int jitter, early_out, scan_mode;
     int tiles_x, tiles_total, shard_rank, shard_count, tiles_local;
-    UnitPlan up;                   // how a tile's samples are cut into work units (rt_units.h)
+    // Work units = (tile, sample chunk).  A tile's samples are cut into GRADED chunks: lv_n[0] chunks of lv_spp[0] samples
+    // per pixel, then lv_n[1] of lv_spp[1], then lv_n[2] of lv_spp[2] (the very last chunk may be shorter); unit ids are
+    // level-major (every tile's long chunks first), so a launch ends on short units (rt_api.cu: launch_render).
     int chunks, units_local;       // chunks per tile over all levels; units = tiles_local * chunks
+    int lv_n[3], lv_spp[3];
     int compact_out;
     uchar4* out;
     double* sum_out;               // optional W*H*3

@@ -68,8 +68,34 @@ __device__ __forceinline__ TileGeom tile_geom(const RenderArgs& a, int tile_l) {
     g.tw = min(kTileW, a.W - g.x0); g.th = min(kTileH, a.H - g.y0);
     return g;
 }
-// Graded chunks (rt_units.h): unit id -> (tile, chunk of that tile), chunk -> first sample and samples per pixel.
-__device__ __forceinline__ int unit_spp(const RenderArgs& a, int chunk) { return chunk_spp(a.up, a.spp, chunk); }
+// Graded chunks (RenderArgs::lv_n / lv_spp): unit id -> (tile, chunk of that tile), chunk -> first sample and length.
+__device__ __forceinline__ void unit_of(const RenderArgs& a, unsigned id, int& tile_l, int& chunk) {
+    const unsigned e0 = (unsigned)a.tiles_local * (unsigned)a.lv_n[0], e1 = e0 + (unsigned)a.tiles_local * (unsigned)a.lv_n[1];
+    unsigned j = id, n = (unsigned)a.lv_n[0];
+    int first = 0;
+    if (id >= e0) { j = id - e0; n = (unsigned)a.lv_n[1]; first = a.lv_n[0]; }
+    if (id >= e1) { j = id - e1; n = (unsigned)a.lv_n[2]; first = a.lv_n[0] + a.lv_n[1]; }
+    const unsigned t = j / n;
+    // Tiles are handed out from the LAST row of the frame up: a launch's ramp-down is set by the longest paths of its
+    // last units, and the frames of this renderer have their sky (paths of one cast) at the top and the ground with its
+    // trapped paths (51 casts) at the bottom.  (Any order gives the same frame.)
+#ifndef RT_TILE_REVERSE
+#define RT_TILE_REVERSE 1
+#endif
+    tile_l = RT_TILE_REVERSE ? a.tiles_local - 1 - (int)t : (int)t;
+    chunk = first + (int)(j - t * n);
+}
+__device__ __forceinline__ int chunk_first_sample(const RenderArgs& a, int chunk) {
+    const int k1 = chunk - a.lv_n[0], k2 = k1 - a.lv_n[1];
+    if (k1 < 0) return chunk * a.lv_spp[0];
+    if (k2 < 0) return a.lv_n[0] * a.lv_spp[0] + k1 * a.lv_spp[1];
+    return a.lv_n[0] * a.lv_spp[0] + a.lv_n[1] * a.lv_spp[1] + k2 * a.lv_spp[2];
+}
+__device__ __forceinline__ int unit_spp(const RenderArgs& a, int chunk) {
+    const int k1 = chunk - a.lv_n[0], k2 = k1 - a.lv_n[1];
+    const int len = k1 < 0 ? a.lv_spp[0] : (k2 < 0 ? a.lv_spp[1] : a.lv_spp[2]);
+    return min(len, a.spp - chunk_first_sample(a, chunk));
+}
 
 // write_color's arithmetic (programs/color.h:16-23) for the pixels of a finished tile; coalesced uchar4 rows.
 template <bool kFromGlobal>
@@ -272,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R, kSrc>::kMinBlocks) r
                     id = __shfl_sync(0xffffffffu, id, 0);
                     if (__any_sync(0xffffffffu, id >= (unsigned)a.units_local)) { no_more = true; break; }
                     c.valid = 1;
-                    unit_of(a.up, a.tiles_local, id, c.tile_l, c.chunk);
+                    unit_of(a, id, c.tile_l, c.chunk);
                     const TileGeom g = tile_geom(a, c.tile_l);
                     c.total = (uint32_t)(g.tw * g.th) * (uint32_t)unit_spp(a, c.chunk);
                     c.next = 0;
@@ -286,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R, kSrc>::kMinBlocks) r
                     const uint32_t id = c.next + rank;
                     const uint32_t ns = (uint32_t)unit_spp(a, c.chunk);
                     const uint32_t p = id / ns;
-                    const uint32_t s = (uint32_t)(a.sample_base + chunk_first_sample(a.up, c.chunk)) + (id - p * ns);
+                    const uint32_t s = (uint32_t)(a.sample_base + chunk_first_sample(a, c.chunk)) + (id - p * ns);
                     const int ly = (int)p / g.tw, lx = (int)p - ly * g.tw;
                     const int i = g.x0 + lx, j = a.H - 1 - (g.y0 + ly);  // j from the bottom (programs/main.cc:72)
                     const uint32_t pixid = (uint32_t)(j * a.W + i);
@@ -496,10 +522,10 @@ __global__ void __launch_bounds__(kWaveThreads, RT_WAVE_MINB) render_wave_kernel
                 id = __shfl_sync(0xffffffffu, id, 0);
                 if (id >= (unsigned)a.units_local) { no_more = true; break; }
                 c.valid = 1;
-                unit_of(a.up, a.tiles_local, id, c.tile_l, c.chunk);
+                unit_of(a, id, c.tile_l, c.chunk);
                 geo = tile_geom(a, c.tile_l);
                 unit_ns = (uint32_t)unit_spp(a, c.chunk);
-                unit_s0 = (uint32_t)(a.sample_base + chunk_first_sample(a.up, c.chunk));
+                unit_s0 = (uint32_t)(a.sample_base + chunk_first_sample(a, c.chunk));
                 c.total = (uint32_t)(geo.tw * geo.th) * unit_ns;
                 c.next = 0;
                 cur = np;

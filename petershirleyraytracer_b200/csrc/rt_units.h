@@ -30,6 +30,11 @@ struct UnitPlan {
     int lv_spp[3];  // samples per pixel of a chunk of that level
 };
 
+// The decode functions below are the host's statement of what the kernels do with RenderArgs::lv_n / lv_spp
+// (rt_kernels.cuh: unit_of, chunk_first_sample, unit_spp -- kept there verbatim: the register allocation of the scan
+// kernel, and with it 2.7 % of its speed, turned out to depend on where these few lines are compiled from,
+// profiles/r2_ab_refactor.txt).  tests/cpp/units_test.cc sweeps this copy; the GPU suite checks the kernels' copy by
+// rendering graded, ungraded and single-chunk frames that must agree bit for bit.
 RT_HD inline int plan_chunks(const UnitPlan& u) { return u.lv_n[0] + u.lv_n[1] + u.lv_n[2]; }
 
 RT_HD inline int chunk_first_sample(const UnitPlan& u, int chunk) {
@@ -46,9 +51,6 @@ RT_HD inline int chunk_spp(const UnitPlan& u, int spp, int chunk) {
     return len < left ? len : left;
 }
 
-#ifndef RT_TILE_REVERSE
-#define RT_TILE_REVERSE 1
-#endif
 // unit id -> (tile of this shard, chunk of that tile)
 RT_HD inline void unit_of(const UnitPlan& u, int tiles_local, unsigned id, int& tile_l, int& chunk) {
     const unsigned e0 = (unsigned)tiles_local * (unsigned)u.lv_n[0], e1 = e0 + (unsigned)tiles_local * (unsigned)u.lv_n[1];
@@ -57,7 +59,7 @@ RT_HD inline void unit_of(const UnitPlan& u, int tiles_local, unsigned id, int& 
     if (id >= e0) { j = id - e0; n = (unsigned)u.lv_n[1]; first = u.lv_n[0]; }
     if (id >= e1) { j = id - e1; n = (unsigned)u.lv_n[2]; first = u.lv_n[0] + u.lv_n[1]; }
     const unsigned t = j / n;
-    tile_l = RT_TILE_REVERSE ? tiles_local - 1 - (int)t : (int)t;
+    tile_l = tiles_local - 1 - (int)t;   // last tile row first
     chunk = first + (int)(j - t * n);
 }
 

@@ -21,3 +21,15 @@ with rt.Scene(c, r) as sc:
                 best = st
         print(json.dumps(dict(kw=kw, ms=round(best["kernel_ms"], 2), msamples_s=round(best["samples"] / best["kernel_ms"] / 1e3, 1),
                               md5=hashlib.md5(rgba.tobytes()).hexdigest()[:12])), flush=True)
+
+dc, dr = scenes.default_scene()
+with rt.Scene(dc, dr) as sc:
+    cam1 = rt.Camera.default()
+    p = rt.make_params(400, 225, 100, 50, seed=1, scan_mode=0, early_out=False)
+    best = None
+    for _ in range(5):
+        rgba, _, st = rt.render(sc, cam1, p)
+        if best is None or st["kernel_ms"] < best["kernel_ms"]:
+            best = st
+    print(json.dumps(dict(kw="c1", ms=round(best["kernel_ms"], 3), msamples_s=round(best["samples"] / best["kernel_ms"] / 1e3, 1),
+                          md5=hashlib.md5(rgba.tobytes()).hexdigest()[:12])), flush=True)
