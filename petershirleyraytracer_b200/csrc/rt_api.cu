@@ -284,7 +284,11 @@ int launch_render(rt_scene* sc, const rt_camera* cam, const rt_params* p, void* 
     int threads = rt::kThreads;
     void (*kern)(const rt::RenderArgs) = nullptr;
     if (mode == RT_SCAN_BVH && p->reserved[2] == 2) kern = rt::render_kernel<1, 2>;   // round-1 traversal kernel (A/B evidence only)
-    else if (mode == RT_SCAN_BVH) { kern = rt::render_wave_kernel; S.total = rt::wave_smem().total; threads = rt::kWaveThreads; }
+    else if (mode == RT_SCAN_BVH) {
+        // tie-grid candidates in straight-line code once the FP32 sphere array outgrows L1 (rt_device.cuh: self_cast_flat)
+        kern = sc->n > 4096 ? rt::render_wave_kernel<true> : rt::render_wave_kernel<false>;
+        S.total = rt::wave_smem().total; threads = rt::kWaveThreads;
+    }
     else if (use_const) kern = R == 1 ? rt::render_kernel<1, 1> : (R == 2 ? rt::render_kernel<2, 1> : rt::render_kernel<4, 1>);
     else kern = R == 1 ? rt::render_kernel<1, 0> : (R == 2 ? rt::render_kernel<2, 0> : rt::render_kernel<4, 0>);
     if (const char* e = std::getenv("RT_SMEM_PAD")) S.total += (uint32_t)std::atoi(e);   // tuning experiments only: fewer CTAs per SM

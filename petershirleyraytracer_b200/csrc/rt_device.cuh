@@ -686,7 +686,7 @@ __device__ __forceinline__ bool tie_candidate(const float4 s, float fx, float fy
 // FP32 shell tests of ALL candidates in straight-line code (their loads are in flight together); only candidates that
 // pass (0.3 % of the casts) set their bit and cost another trip.  (Round 2, first form: one trip per candidate, shell
 // test or not -- 4-5 trips per warp and one dependent load each.)
-__device__ __forceinline__ bool self_cast(const SceneDev& sc, int self, double ox, double oy, double oz, double dx,
+__device__ __forceinline__ bool self_cast_flat(const SceneDev& sc, int self, double ox, double oy, double oz, double dx,
                                           double dy, double dz, double A, double tmin, Best& best, uint32_t& n_exact) {
     if (self < 0) return false;
     const RcpA dA = make_rcp(A);
@@ -738,6 +738,65 @@ __device__ __forceinline__ bool self_cast(const SceneDev& sc, int self, double o
         }
     }
     return decided;
+}
+
+// The same step with one trip per candidate -- entry 0 is the start sphere, then the giants, then the cell's spheres,
+// each with its own load and shell test.  Fewer instructions per trip, dependent loads: the faster form while the FP32
+// sphere array stays in L1 (small scenes: C3 with the early-out +3.5 %, the default scene +7 %), the slower one when it
+// does not (C4: -7 %); profiles/r2_ab_wave2.txt.  The wavefront kernel is instantiated with both (kTieFlat).
+__device__ __forceinline__ bool self_cast_loop(const SceneDev& sc, int self, double ox, double oy, double oz, double dx,
+                                          double dy, double dz, double A, double tmin, Best& best, uint32_t& n_exact) {
+    if (self < 0) return false;
+    const RcpA dA = make_rcp(A);
+    const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+    bool decided = false;
+    int ncand = 1;
+    int4 cell = make_int4(-1, -1, -1, -1);
+    float fx = 0.f, fy = 0.f, fz = 0.f, o2 = 0.f, rho = 0.f;
+#pragma unroll 1
+    for (int e = 0; e < ncand; ++e) {
+        int j = self;
+        bool test = true;
+        if (e > 0) {
+            const int g = e - 1 - sc.tie_ngiants;
+            if (g < 0) j = sc.tie_giants[e - 1];
+            else j = g == 0 ? cell.x : (g == 1 ? cell.y : (g == 2 ? cell.z : cell.w));
+            test = j != self && tie_candidate(__ldg(sc.sph32 + j), fx, fy, fz, o2, rho);
+        }
+        if (test) {
+            ++n_exact;
+            exact_test_unordered(sc.exact, j, ox, oy, oz, dx, dy, dz, dA, tmin, kInf, best);
+        }
+        if (e == 0) {
+            if (!(sc.tie_ok && best.k == self && dA.fast)) break;
+            if (best.t != 0.0) {   // reach = t * |dir|, rounded up
+                rho = __fmul_ru(__fmul_ru(__double2float_ru(best.t), __fsqrt_ru(__double2float_ru(A))), 1.0000019f);
+                if (!(rho <= sc.tie_rho_max)) break;   // (also NaN / negative t)
+            }
+            fx = (float)ox; fy = (float)oy; fz = (float)oz;
+            o2 = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
+            int ncell = 0;
+            const bool inside = fx >= sc.tie_g0[0] && fx <= sc.tie_g1[0] && fy >= sc.tie_g0[1] && fy <= sc.tie_g1[1] &&
+                                fz >= sc.tie_g0[2] && fz <= sc.tie_g1[2];
+            if (inside) {   // outside the grid no listed sphere has its (padded) box around o
+                const int ix = (int)((fx - sc.tie_g0[0]) * sc.tie_inv_h), iy = (int)((fy - sc.tie_g0[1]) * sc.tie_inv_h),
+                          iz = (int)((fz - sc.tie_g0[2]) * sc.tie_inv_h);
+                cell = __ldg(sc.tie_cells + ((size_t)iz * sc.tie_dimy + iy) * sc.tie_dimx + ix);
+                if (cell.x == -2) break;   // overfull cell
+                ncell = (cell.x >= 0) + (cell.y >= 0) + (cell.z >= 0) + (cell.w >= 0);   // (entries fill from .x up)
+            }
+            ncand = 1 + sc.tie_ngiants + ncell;
+            decided = true;
+        }
+    }
+    return decided;
+}
+
+template <bool kFlat>
+__device__ __forceinline__ bool self_cast(const SceneDev& sc, int self, double ox, double oy, double oz, double dx, double dy,
+                                          double dz, double A, double tmin, Best& best, uint32_t& n_exact) {
+    return kFlat ? self_cast_flat(sc, self, ox, oy, oz, dx, dy, dz, A, tmin, best, n_exact)
+                 : self_cast_loop(sc, self, ox, oy, oz, dx, dy, dz, A, tmin, best, n_exact);
 }
 
 // hittable_list::hit for one ray given its survivors (or the full list when ovf): list order, shrinking tmax.

@@ -471,6 +471,8 @@ __host__ __device__ inline WaveSmem wave_smem() {
 #ifndef RT_WAVE_MINB
 #define RT_WAVE_MINB 4   // 128 registers: at 5 CTAs/SM (96) the two phases spill ~230 bytes and run 12 % slower
 #endif
+// kTieFlat: the start-sphere step tests all tie-grid candidates in straight-line code (large scenes), or one per trip
+template <bool kTieFlat>
 __global__ void __launch_bounds__(kWaveThreads, RT_WAVE_MINB) render_wave_kernel(const __grid_constant__ RenderArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const WaveSmem L = wave_smem();
@@ -634,7 +636,7 @@ __global__ void __launch_bounds__(kWaveThreads, RT_WAVE_MINB) render_wave_kernel
                             nb.t = kInf; nb.C = 1.0; nb.k = -1;
                             bool decided = false;
                             if (sane && a.tmin >= 0.0)   // (other rays: the T phase runs the sequential FP64 scan)
-                                decided = self_cast(a.sc, hitb.k, rc.px, rc.py, rc.pz, ndx, ndy, ndz, A2, a.tmin, nb, n_exact);
+                                decided = self_cast<kTieFlat>(a.sc, hitb.k, rc.px, rc.py, rc.pz, ndx, ndy, ndz, A2, a.tmin, nb, n_exact);
                             bt[rec] = nb.t;
                             bk[rec] = nb.k < 0 ? -1 : (nb.k | (nb.C == 0.0 ? (1 << 30) : 0));
                             selfk[rec] = hitb.k;
@@ -741,7 +743,7 @@ __device__ __forceinline__ Best cast_one(const SceneDev& sc, const float4* s_fil
             bool deep = false;
             uint32_t n_nodes = 0;
             if (ok) {
-                if (tmax == kInf && self_cast(sc, self, ox, oy, oz, dx, dy, dz, A, tmin, best, n_exact)) { ++n_self; return best; }
+                if (tmax == kInf && self_cast<false>(sc, self, ox, oy, oz, dx, dy, dz, A, tmin, best, n_exact)) { ++n_self; return best; }
                 bvh_cast(sc, ox, oy, oz, dx, dy, dz, A, tmin, tmax, best, self, n_exact, n_nodes, deep);
             }
             if (!ok || deep) {
