@@ -13,6 +13,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -429,8 +430,12 @@ int fill_scene(rt_scene* sc, const double* centres_xyz, const double* radii, boo
     std::thread tie_thread;
     int host_threads = 0;   // 0: what the host offers
     if (const char* e = std::getenv("RT_HOST_THREADS")) host_threads = std::atoi(e);   // tuning experiments only (1: sequential build)
-    if (n >= 4096 && host_threads != 1) tie_thread = std::thread([&] { rt::build_tie_grid(centres_xyz, radii, n, &sc->tie); });
-    else rt::build_tie_grid(centres_xyz, radii, n, &sc->tie);
+    bool tie_inline = !(n >= 4096 && host_threads != 1);
+    if (!tie_inline) {
+        try { tie_thread = std::thread([&] { rt::build_tie_grid(centres_xyz, radii, n, &sc->tie); }); }
+        catch (const std::system_error&) { tie_inline = true; }   // no thread to be had: build it here
+    }
+    if (tie_inline) rt::build_tie_grid(centres_xyz, radii, n, &sc->tie);
     struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{tie_thread};   // (also on the error returns)
     if (refit && have_tree) {
         rt::refit_bvh(centres_xyz, radii, &sc->bvh_host);

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -210,11 +211,13 @@ struct Builder {
         if (fork > 0 && kBvhLeafMax == 1 && count >= 4096) {
             std::vector<BvhNode> left;
             int32_t c0_local = 0;
-            std::thread th([&] { b0 = bounds(first, mid); c0_local = build(left, first, mid, depth + 1, fork - 1); });
+            auto build_left = [&] { b0 = bounds(first, mid); c0_local = build(left, first, mid, depth + 1, fork - 1); };
+            std::thread th;
+            try { th = std::thread(build_left); } catch (const std::system_error&) {}   // no thread to be had: build it here
             b1 = bounds(first + mid, count - mid);
             std::vector<BvhNode> right;
             const int32_t c1_local = build(right, first + mid, count - mid, depth + 1, fork - 1);
-            th.join();
+            if (th.joinable()) th.join(); else build_left();
             auto splice = [&](std::vector<BvhNode>& sub, int32_t ref) {
                 const int32_t off = (int32_t)nodes.size();
                 for (BvhNode& n : sub) {
