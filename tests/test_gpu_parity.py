@@ -544,6 +544,30 @@ def test_cull_and_boxes_are_conservative_at_scale(rt, book):
     assert np.array_equal(a_acc, b_acc) and np.array_equal(a_img, b_img)
 
 
+def test_packed_scan_equals_scalar_scan_and_fp64_scan_at_scale(rt, book):
+    """The constant-bank scan tests two spheres per instruction (fma.rn.f32x2); each half is the scalar FP32 fma of the
+    same operands, so its survivors -- and with them every integer sum and counter -- must equal those of the scalar scan
+    (the TMA-staged shared-memory variant still runs it) over tens of millions of casts, and both must equal the mode that
+    culls nothing (FP64 test of every sphere)."""
+    from petershirleyraytracer_b200 import scenes
+    c, r = book
+    W, H, spp = 600, 400, 8
+    cam = scenes.book_camera(W, H)
+    with rt.Scene(c, r) as sc:
+        kw = dict(seed=12, early_out=False)
+        a_acc, a_img, a_st = rt.render_pass(sc, cam, rt.make_params(W, H, spp, 50, scan_mode=0, **kw), 0)
+        b_acc, b_img, b_st = rt.render_pass(sc, cam, rt.make_params(W, H, spp, 50, scan_mode=0, cull_smem=True, **kw), 0)
+        assert a_st["casts"] > 45_000_000
+        for k in ("casts", "black", "primary_hits", "exact_tests", "overflows"):
+            assert a_st[k] == b_st[k], k       # (exact_tests: the same survivors, not just the same hits)
+        assert np.array_equal(a_acc, b_acc) and np.array_equal(a_img, b_img)
+        Ws, Hs = 150, 100
+        cams = scenes.book_camera(Ws, Hs)
+        p_acc, p_img, p_st = rt.render_pass(sc, cams, rt.make_params(Ws, Hs, spp, 50, scan_mode=0, **kw), 0)
+        e_acc, e_img, e_st = rt.render_pass(sc, cams, rt.make_params(Ws, Hs, spp, 50, scan_mode=1, **kw), 0)
+        assert p_st["casts"] == e_st["casts"] and np.array_equal(p_acc, e_acc) and np.array_equal(p_img, e_img)
+
+
 def test_bvh_100k_spheres_config4(rt):
     """BASELINE config 4 scene (~99.9k spheres): primary hits vs the oracle's list scan, and a small render vs
     the FP64-everything mode."""
