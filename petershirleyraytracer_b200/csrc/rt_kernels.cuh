@@ -163,6 +163,29 @@ __device__ __forceinline__ void flush_unit(const RenderArgs& a, const Unit& u, u
     for (int j = 0; j < kTilePix * 3 / 32; ++j) accp[j * 32 + lane] = 0ull;
 }
 
+#ifndef RT_COOP_OVERFLOW
+#define RT_COOP_OVERFLOW 1
+#endif
+// hittable_list::hit for ONE ray by the whole warp: lane i runs the FP64 sphere::hit of spheres i, i + 32, ... on the
+// fixed interval [tmin, tmax], then five butterfly steps keep the smallest accepted t and, on equal t, the later list
+// index (hittable_list.cc:9-17 in its order-independent form).  Returns the winning list index to every lane, -1 = miss.
+// (The candidate lists hold 16-bit indices: the linear scan serves at most kMaxLinearSmem spheres.)
+__device__ __noinline__ int coop_list_scan(const SceneDev& sc, int lane, double ox, double oy, double oz, double dx, double dy,
+                                           double dz, double A, double tmin, double tmax) {
+    Best best;
+    best.t = tmax; best.C = 1.0; best.k = -1;
+    const RcpA dA = make_rcp(A);
+#pragma unroll 1
+    for (int k = lane; k < sc.n; k += 32) exact_test_unordered(sc.exact, k, ox, oy, oz, dx, dy, dz, dA, tmin, tmax, best);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double t2 = __shfl_xor_sync(0xffffffffu, best.t, o);
+        const int k2 = __shfl_xor_sync(0xffffffffu, best.k, o);
+        if (k2 >= 0 && (best.k < 0 || t2 < best.t || (t2 == best.t && k2 > best.k))) { best.t = t2; best.k = k2; }
+    }
+    return best.k;
+}
+
 template <int R, int kSrc>
 struct RenderTraits {
 #ifndef RT_MINB1
@@ -227,6 +250,30 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R, kSrc>::kMinBlocks) r
 #pragma unroll 1
         for (int r = 0; r < R; ++r) {
             const uint32_t bit = 1u << r;
+#if RT_COOP_OVERFLOW
+            if (!kBvh) {
+                // A cast whose survivor list overflowed (grazing rays along a sphere row: 0.016 % of the casts, but 1 % of
+                // the rounds have one) needs the FP64 test of EVERY sphere.  One lane doing that alone holds the warp for
+                // n trips; instead the warp scans the list for that lane's ray, 32 spheres per trip, and reduces to the
+                // winner of hittable_list.cc:9-17 (smallest accepted t, later index on ties: order-independent, see
+                // exact_test_unordered).  The winner becomes the lane's only candidate and takes the ordinary path below.
+                unsigned om = __ballot_sync(0xffffffffu, (alive_mask & bit) && ((cntpack >> (8 * r + 7)) & 1u) && a.scan_mode == 0);
+                while (om) {
+                    const int L = __ffs((int)om) - 1;
+                    om &= om - 1u;
+                    const double* sl = st + (L - lane);   // lane L's path state (shared memory: a broadcast read)
+                    const double ox = sl[(0 * R + r) * kThreads], oy = sl[(1 * R + r) * kThreads], oz = sl[(2 * R + r) * kThreads];
+                    const double dx = sl[(3 * R + r) * kThreads], dy = sl[(4 * R + r) * kThreads], dz = sl[(5 * R + r) * kThreads];
+                    const int kw = coop_list_scan(a.sc, lane, ox, oy, oz, dx, dy, dz, ddot(dx, dy, dz, dx, dy, dz), a.tmin, kInf);
+                    if (lane == L) {
+                        if (kw >= 0) cand[(0 * R + r) * kThreads] = (uint16_t)kw;
+                        cntpack = (cntpack & ~(0xffu << (8 * r))) | ((kw >= 0 ? 1u : 0u) << (8 * r));
+                        ++n_ovf;
+                        n_exact += (uint32_t)a.sc.n;
+                    }
+                }
+            }
+#endif
             if (alive_mask & bit) {
                 const double ox = st[(0 * R + r) * kThreads], oy = st[(1 * R + r) * kThreads], oz = st[(2 * R + r) * kThreads];
                 const double dx = st[(3 * R + r) * kThreads], dy = st[(4 * R + r) * kThreads], dz = st[(5 * R + r) * kThreads];
@@ -237,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, RenderTraits<R, kSrc>::kMinBlocks) r
                 const int cnt = (int)((cntpack >> (8 * r)) & 0x7fu);
                 const bool ovf = ((cntpack >> (8 * r + 7)) & 1u) != 0;
                 ++n_casts;
-                if (ovf && a.scan_mode == 0) ++n_ovf;
+                if (ovf && a.scan_mode == 0 && (kBvh || !RT_COOP_OVERFLOW)) ++n_ovf;
                 Best best = pending[0];
 #pragma unroll
                 for (int q = 1; q < R; ++q) if (r == q) best = pending[q];
