@@ -405,7 +405,7 @@ def main():
             owl = workload(name)
             ob = GpuBench(owl, rt, torch, dist, world, rank, local, deal=args.deal)
             mode = rt.SCAN_BVH if ob.big else rt.SCAN_FILTERED
-            nst = 1 if name == "c5" else 2
+            nst = {"c5": 1, "c1": 10}.get(name, 2)   # (c1 is an 8 ms frame: more steps, or launch jitter shows in the figure)
             warm = ob.params(mode, False, spp=max(1, owl["spp"] // 64))      # (a short frame warms caches / clocks; the timed steps are full frames)
             leg = ob.timed(ob.params(mode, False), nst, 1, flush, warm_p=warm)
             entry = {"config": config_dict(owl, world), "scan_mode": "bvh" if ob.big else "linear cull scan",
@@ -431,7 +431,7 @@ def main():
                             "instructions (+ BVH box tests x 14) x 2 flop / render-kernel time (CUDA events on the launching stream, "
                             "avg over the timed launches, per GPU); peak = FFMA rate measured in this run by rt_measure_fp32_peak, "
                             "peak_nominal = 148 SMs x 128 lanes x 1.965 GHz x 2 (MEASURED_PEAKS.json has no FP32 figure); the scan "
-                            "loop itself issues 7 FMA-pipe + ~1.9 other instructions per test")
+                            "loop itself issues 3.5 packed FFMA2 (= 7 FMAs) + ~2.3 other instructions per test")
         roofline["with_early_out"] = {"msamples_s": eo["value"], "casts_per_sample": eo["counts"]["casts"] / max(eo["counts"]["samples"], 1)}
         cpu = cpu1 = cpu_own = None
         if world == 1 and not args.no_cpu_baseline and not b.big:   # (the reference's O(N) scan of 1e5 spheres: ~1 ms per cast)
