@@ -86,7 +86,10 @@ typedef struct {
                                     EXACT = FP64 test of every sphere (validation); BVH; AUTO */
     int32_t shard_rank;          /* multi-GPU: this call renders tiles t with t % shard_count == shard_rank */
     int32_t shard_count;         /* 1 = whole frame */
-    int32_t reserved[3];
+    int32_t reserved[3];         /* 0 = defaults.  Tuning / A-B knobs that never change the frame: [0] paths per lane of the
+                                    linear scan (1, 2, 4); [1] work units: n > 0 = n equal sample chunks per tile, -1 = automatic
+                                    length but ungraded, -(10 + F) = short level of F/4 long units per warp (csrc/rt_units.h);
+                                    [2] 1 = cull array from TMA-staged shared memory, 2 = round-1 BVH kernel, 3 = no tie grid */
     /* ABI 3: the constants ray_color hard-codes.  custom_shading == 0 (a zero-filled struct)
      * renders with the reference's values and ignores the four fields below, so the default path stays the
      * reference bit for bit. */
