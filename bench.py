@@ -406,7 +406,9 @@ def main():
             ob = GpuBench(owl, rt, torch, dist, world, rank, local, deal=args.deal)
             mode = rt.SCAN_BVH if ob.big else rt.SCAN_FILTERED
             nst = {"c5": 1, "c1": 10}.get(name, 2)   # (c1 is an 8 ms frame: more steps, or launch jitter shows in the figure)
-            warm = ob.params(mode, False, spp=max(1, owl["spp"] // 64))      # (a short frame warms caches / clocks; the timed steps are full frames)
+            # (a short frame warms caches / clocks; the timed steps are full frames.  c1's frame takes 8 ms: warm up with the
+            #  frame itself, or the first timed step allocates the per-tile sums a 1 spp frame never needs)
+            warm = None if name == "c1" else ob.params(mode, False, spp=max(1, owl["spp"] // 64))
             leg = ob.timed(ob.params(mode, False), nst, 1, flush, warm_p=warm)
             entry = {"config": config_dict(owl, world), "scan_mode": "bvh" if ob.big else "linear cull scan",
                      "value": leg["value"], "unit": "Msamples/s", "steps": nst, "ms_per_step": leg["ms"] / nst,
